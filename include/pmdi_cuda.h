@@ -34,8 +34,7 @@ extern "C" {
 #define PMDI_SWEEP_DEBUG        1u /* capture per-step lp / log-weights / allocations / ancestors */
 #define PMDI_SWEEP_SSTAR_COMPAT 2u /* emit allocations without following ancestors, as pmdi() does
                                       (src/pmdi.jl:321-324; the tested twin src/__pmdi.jl:285 follows them) */
-#define PMDI_SWEEP_NO_GRAPH     4u /* launch kernels one by one instead of replaying CUDA graphs   */
-#define PMDI_SWEEP_TIME_KERNELS 8u /* CUDA-event pair around every step-kernel launch (implies NO_GRAPH) */
+#define PMDI_SWEEP_TIME_PHASES  4u /* CTA 0 accumulates per-phase wall time of the sweep kernel (globaltimer) */
 
 typedef struct pmdi_ctx pmdi_ctx;
 
@@ -94,11 +93,15 @@ typedef struct pmdi_sweep_out {
   int64_t* p_star;        /* 1-based selected particle (src/pmdi.jl:350)                      */
   double*  logweight;     /* P log-weights before the final reset (src/pmdi.jl:345), may be NULL */
   int64_t  n_resamples;   /* resampling events in this sweep                                  */
-  int64_t  n_evals;       /* dense particle*cluster*feature evaluations performed             */
   int64_t  n_copies;      /* particle stat blocks moved by resampling                         */
-  double   device_ms;     /* device time of the sweep proper (prefix .. selection), CUDA events */
-  double   step_kernel_ms;   /* with PMDI_SWEEP_TIME_KERNELS: summed duration of the step kernel */
-  int64_t  step_kernel_launches;
+  int64_t  n_evals;       /* particle*cluster*feature predictive terms actually evaluated (occupied
+                             clusters only; every empty label shares one evaluation per step) */
+  int64_t  n_evals_dense; /* steps * P * N * sum_k D_k: the dense count of SURVEY.md 8(d)      */
+  int64_t  rows_evaluated[8]; /* per dataset: cluster rows evaluated over the sweep           */
+  double   device_ms;     /* device time of the whole sweep (prefix .. selection), CUDA events */
+  double   sweep_kernel_ms;  /* device time of the persistent per-observation kernel alone    */
+  double   phase_ms[6];   /* with PMDI_SWEEP_TIME_PHASES, CTA 0: 0 staging+row list, 1 predictive,
+                             2 barrier wait, 3 proposal, 4 ESS+add, 5 resampling              */
   /* debug capture, used when PMDI_SWEEP_DEBUG is set; each may be NULL */
   double*  dbg_lp;        /* [steps][K][P][N]                                                 */
   double*  dbg_lw;        /* [steps][P] after coupling, before resampling                     */

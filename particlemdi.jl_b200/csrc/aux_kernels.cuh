@@ -1,0 +1,317 @@
+// Kernels around the persistent sweep: state initialisation, the rho-prefix build
+// (src/pmdi.jl:188-207), particle selection + lineage back-trace (src/pmdi.jl:345-350,373),
+// the feature-selection log-marginal reduction (src/pmdi.jl:120-128,354-370) and the
+// single-cluster evaluation used by the plugin-contract parity tests.
+#pragma once
+#include "cluster_types.cuh"
+
+// all rows of a dataset to the empty-cluster state (constructors gaussian_cluster.jl:17-21,
+// categorical_cluster.jl:6-10, negbinom_cluster.jl:9-10)
+__global__ void k_init_rows(DsDev ds, long long rows) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (ds.type == T_GAUSSIAN) {
+    for (long long i = t0; i < rows * ds.Dp; i += stride) {
+      ds.mu[i] = 0.0; ds.lamn[i] = 1.0; ds.sum[i] = 0.0; ds.beta[i] = 0.5;
+    }
+  } else if (ds.type == T_CATEGORICAL) {
+    for (long long i = t0; i < rows * ds.Lmax * ds.Dp; i += stride) ds.cnt[i] = 0u;
+  } else {
+    for (long long i = t0; i < rows * ds.Dp; i += stride) ds.S[i] = 0;
+  }
+  for (long long i = t0; i < rows * ds.J; i += stride) { ds.aux[i] = 0.0; ds.part[i] = 0.0; }
+  for (long long i = t0; i < rows; i += stride) ds.n[i] = 0;
+}
+
+__global__ void k_sweep_init(SweepParams sp) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < sp.P) {
+    sp.lw[t] = sp.lw_init;
+    sp.slot_of[t] = t;
+    sp.slot_of[sp.P + t] = t;
+  }
+  if (t == 0) {
+    *sp.bar = 0u;
+    *sp.err = 0;
+    sp.counters[0] = sp.counters[1] = sp.counters[2] = 0;
+    sp.plan_out[0] = 0;
+    for (int k = 0; k < PMDI_MAX_K; ++k) sp.rows_eval[k] = 0ull;
+  }
+}
+
+// Members of every label among the first n1-1 shuffled observations, in shuffle order
+// (src/pmdi.jl:193,200-206).  One block per dataset, thread m = label m+1.
+__global__ void k_prefix_lists(SweepParams sp, int* members /* [K][n1-1] */, int* off /* [K][N+1] */) {
+  const int k = blockIdx.x, m = threadIdx.x, N = sp.N, npre = sp.n1 - 1;
+  __shared__ int cnt[PMDI_MAX_N + 1];
+  const long long* s = sp.s_in + (size_t)k * sp.n_obs;
+  int c = 0;
+  if (m < N)
+    for (int t = 0; t < npre; ++t) c += ((int)s[sp.order[t]] - 1 == m);
+  if (m < N) cnt[m] = c;
+  __syncthreads();
+  if (m == 0) {
+    int acc = 0;
+    for (int i = 0; i < N; ++i) { const int v = cnt[i]; cnt[i] = acc; acc += v; }
+    cnt[N] = acc;
+  }
+  __syncthreads();
+  if (m <= N) off[k * (N + 1) + m] = cnt[m];
+  if (m < N) {
+    int w = cnt[m];
+    for (int t = 0; t < npre; ++t) {
+      const int i = sp.order[t];
+      if ((int)s[i] - 1 == m) members[(size_t)k * npre + (w++)] = i;
+    }
+  }
+}
+
+// Sequential cluster_add! of the members of one label into row (slot*N + m), one thread per
+// feature (literal arithmetic, same bits as the reference).  use_flags = 0 -> all features on.
+__device__ __forceinline__ void build_row_feature(const DsDev& ds, long long row, int q,
+                                                  const int* mem, int cnt, int use_flags) {
+  const bool on = use_flags ? (ds.flag[q] != 0) : (q < ds.D);
+  if (ds.type == T_GAUSSIAN) {
+    double sum = 0.0, beta = 0.5, mu = 0.0, lam = 1.0;
+    if (on) {
+      const double* x = (const double*)ds.x;
+      for (int t = 0; t < cnt; ++t) {
+        const double nn = (double)(t + 1);
+        const double xv = x[(size_t)mem[t] * ds.Dp + q];
+        sum = __dadd_rn(sum, xv);
+        const double dd = __dadd_rn(xv, -mu);
+        beta = __dadd_rn(beta, __ddiv_rn(__dmul_rn(__dadd_rn(__dadd_rn(nn, -1.0), 0.001), __dmul_rn(dd, dd)),
+                                         __dmul_rn(2.0, __dadd_rn(nn, 0.001))));
+        mu = __ddiv_rn(sum, __dadd_rn(nn, 0.001));
+        lam = __ddiv_rn(__dmul_rn(__dadd_rn(__dmul_rn(0.5, nn), 0.5), __dadd_rn(nn, 0.001)),
+                        __dmul_rn(beta, __dadd_rn(nn, 1.001)));
+      }
+    }
+    const long long o = row * ds.Dp + q;
+    ds.sum[o] = sum; ds.beta[o] = beta; ds.mu[o] = mu;
+    ds.lamn[o] = __ddiv_rn(lam, __dadd_rn((double)cnt, 1.0));
+    if (!on || cnt == 0) ds.lamn[o] = 1.0;
+  } else if (ds.type == T_CATEGORICAL) {
+    uint32_t* c = ds.cnt + row * (long long)ds.Lmax * ds.Dp + q;
+    for (int l = 0; l < ds.Lmax; ++l) c[(long long)l * ds.Dp] = 0u;
+    if (on) {
+      const int* x = (const int*)ds.x;
+      for (int t = 0; t < cnt; ++t) {
+        const int lv = x[(size_t)mem[t] * ds.Dp + q];
+        c[(long long)(lv - 1) * ds.Dp] += 1u;
+      }
+    }
+  } else {
+    long long S = 0;
+    if (on) {
+      const int* x = (const int*)ds.x;
+      for (int t = 0; t < cnt; ++t) S += x[(size_t)mem[t] * ds.Dp + q];
+    }
+    ds.S[row * ds.Dp + q] = S;
+  }
+}
+
+// grid (ceil(Dp/128), N, K): prototypes of the prefix clusters into slot P
+__global__ void k_prefix_build(SweepParams sp, const int* members, const int* off) {
+  const int k = blockIdx.z, m = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+  const DsDev& ds = sp.ds[k];
+  if (q >= ds.Dp) return;
+  const int b = off[k * (sp.N + 1) + m], e = off[k * (sp.N + 1) + m + 1];
+  const long long row = (long long)sp.P * sp.N + m;
+  build_row_feature(ds, row, q, members + (size_t)k * (sp.n1 - 1) + b, e - b, 1);
+  if (q == 0) ds.n[row] = e - b;
+}
+
+// aux of the prototype rows: grid (N, K), one warp per feature block
+__global__ void k_proto_aux(SweepParams sp) {
+  const int k = blockIdx.y, m = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const DsDev& ds = sp.ds[k];
+  const long long row = (long long)sp.P * sp.N + m;
+  const int n = ds.n[row];
+  for (int j = w; j < ds.J; j += blockDim.x >> 5) {
+    if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);
+    else if (ds.type == T_NEGBINOM) nb_aux_block(ds, row, j, n, lane, sp.lf_glob, sp.lf_T);
+    else if (lane == 0) ds.aux[row * ds.J + j] = 0.0;
+  }
+}
+
+// every particle starts the sweep with the prototypes (src/pmdi.jl:197-199: particle[u,:,k] .= id)
+__global__ void k_broadcast(SweepParams sp) {
+  const int lane = threadIdx.x & 31;
+  const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const long long GW = ((long long)gridDim.x * blockDim.x) >> 5;
+  const long long total = (long long)sp.K * sp.P * sp.N;
+  for (long long idx = gw; idx < total; idx += GW) {
+    const int k = (int)(idx / ((long long)sp.P * sp.N));
+    const long long rem = idx - (long long)k * sp.P * sp.N;
+    const int m = (int)(rem % sp.N);
+    row_copy(sp.ds[k], (long long)sp.P * sp.N + m, rem, lane);
+  }
+}
+
+// Particle selection (StatsBase.sample(1:P, Weights(w)), src/pmdi.jl:345-350), lineage back-trace
+// and s[:] = sstar[p_star,:,:] (src/pmdi.jl:373).  One block.
+__global__ void k_finish(SweepParams sp, int compat, long long* s_out, long long* p_star_out,
+                         double* lw_out, long long* cluster_n, int* cur_at) {
+  const int t = threadIdx.x, NT = blockDim.x, P = sp.P, K = sp.K, N = sp.N;
+  __shared__ double red[32];
+  double mx = -INFINITY;
+  for (int p = t; p < P; p += NT) mx = fmax(mx, sp.lw[p]);
+  mx = warp_max(mx);
+  if ((t & 31) == 0) red[t >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (NT >> 5); ++i) mx = fmax(mx, red[i]);
+  for (int p = t; p < P; p += NT) {
+    sp.sc_w[p] = exp(sp.lw[p] - mx);
+    lw_out[p] = sp.lw[p];
+  }
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int p = 0; p < P; ++p) tot += sp.sc_w[p];
+    const double u = sp.tape_select ? sp.tape_select[0]
+                                    : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_SELECT, 0, 0, 0);
+    const double thr = u * tot;
+    int i = 0;
+    double cw = sp.sc_w[0];
+    while (cw < thr && i < P - 1) { ++i; cw += sp.sc_w[i]; }
+    *p_star_out = i + 1;
+    // lineage of p_star through the resampling events, backwards (src/__pmdi.jl:285)
+    int cur = i;
+    for (int st = sp.steps - 1; st >= 0; --st) {
+      const int ev = sp.ev_of_step[st];
+      if (ev >= 0 && !compat) cur = sp.anc_log[(size_t)ev * P + cur] - 1;
+      cur_at[st] = cur;
+    }
+  }
+  for (size_t i = t; i < (size_t)K * sp.n_obs; i += NT) s_out[i] = sp.s_in[i];
+  __syncthreads();
+  for (int idx = t; idx < sp.steps * K; idx += NT) {
+    const int st = idx / K, k = idx - st * K;
+    const int obs = sp.order[sp.n1 - 1 + st];
+    s_out[(size_t)k * sp.n_obs + obs] = 1 + sp.alloc_log[((size_t)st * K + k) * P + cur_at[st]];
+  }
+  if (cluster_n) {
+    const int ev = (int)sp.counters[2];
+    const int* slot = sp.slot_of + (ev & 1) * P;
+    for (size_t idx = t; idx < (size_t)K * P * N; idx += NT) {
+      const int k = (int)(idx / ((size_t)P * N));
+      const size_t rem = idx - (size_t)k * P * N;
+      const int p = (int)(rem / N), m = (int)(rem % N);
+      cluster_n[idx] = sp.ds[k].n[(long long)slot[p] * N + m];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// calc_logmarginal of clusters rebuilt from member lists, one thread per feature, summed over
+// clusters in list order (src/pmdi.jl:358-366); reference formulas gaussian_cluster.jl:68-83,
+// categorical_cluster.jl:53-66, negbinom_cluster.jl:53-60.
+//   out[q] = base[q]*base_sign + sum_c logmarginal_c[q];  flags_out[q] = (1 - 1/exp(out+1)) > u_q
+// ------------------------------------------------------------------------------------------
+__global__ void k_logmarginal(DsDev ds, int n_clusters, const int* c_off, const int* members,
+                              const double* gauss_cst /* per cluster */, const double* nlevels,
+                              int use_flags,
+                              const double* base, double base_scale, double out_scale, double* out,
+                              uint8_t* flags_out, const double* tape_f, unsigned long long seed,
+                              unsigned iter, int k) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= ds.D) return;
+  double acc = base ? base[q] * base_scale : 0.0;
+  const bool on = use_flags ? (ds.flag[q] != 0) : true;
+  for (int c = 0; c < n_clusters; ++c) {
+    const int* mem = members + c_off[c];
+    const int cnt = c_off[c + 1] - c_off[c];
+    const double n = (double)cnt;
+    double lm;
+    if (ds.type == T_GAUSSIAN) {
+      double sum = 0.0, beta = 0.5, mu = 0.0;
+      const double* x = (const double*)ds.x;
+      if (on)
+        for (int t = 0; t < cnt; ++t) {
+          const double nn = (double)(t + 1);
+          const double xv = x[(size_t)mem[t] * ds.Dp + q];
+          sum = __dadd_rn(sum, xv);
+          const double dd = __dadd_rn(xv, -mu);
+          beta = __dadd_rn(beta, __ddiv_rn(__dmul_rn(__dadd_rn(__dadd_rn(nn, -1.0), 0.001), __dmul_rn(dd, dd)),
+                                           __dmul_rn(2.0, __dadd_rn(nn, 0.001))));
+          mu = __ddiv_rn(sum, __dadd_rn(nn, 0.001));
+        }
+      lm = -(n / 2 + 0.5) * log(beta) + gauss_cst[c];
+    } else if (ds.type == T_CATEGORICAL) {
+      const int* x = (const int*)ds.x;
+      const double nl = nlevels[q];  // 0.5 * column maximum (categorical_cluster.jl:10)
+      const int R = (int)(2.0 * nl);
+      lm = lgamma(nl * 2) - lgamma(nl * 2 + n);
+      for (int r = 1; r <= R; ++r) {
+        int cr = 0;
+        if (on)
+          for (int t = 0; t < cnt; ++t) cr += (x[(size_t)mem[t] * ds.Dp + q] == r);
+        lm += lgamma((double)cr + 0.5);
+      }
+    } else {
+      const int* x = (const int*)ds.x;
+      long long S = 0;
+      if (on)
+        for (int t = 0; t < cnt; ++t) S += x[(size_t)mem[t] * ds.Dp + q];
+      lm = lgamma((double)S + 1.0) - lgamma((double)S + (n + 1 + 1)) + lgamma(1.0 + n);
+    }
+    acc += lm;
+  }
+  acc *= out_scale;
+  out[q] = acc;
+  if (flags_out) {
+    const double u = tape_f ? tape_f[q] : pmdi_philox_uniform(seed, iter, DRAW_FEATURE, 0, k, q);
+    flags_out[q] = ((1.0 - 1.0 / exp(acc + 1.0)) > u) ? 1 : 0;
+  }
+}
+
+// calc_logprob of observation `obs` against the prototype row (slot P, label 0), through the
+// same block operators the sweep uses.  One warp; dynamic smem = staged observation row.
+__global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
+  extern __shared__ __align__(16) unsigned char xs_raw[];
+  const DsDev& ds = sp.ds[k];
+  const int lane = threadIdx.x;
+  if (ds.type == T_GAUSSIAN) {
+    const double* src = (const double*)ds.x + (size_t)obs * ds.Dp;
+    for (int q = lane; q < ds.Dp; q += 32) ((double*)xs_raw)[q] = src[q];
+  } else {
+    const int* src = (const int*)ds.x + (size_t)obs * ds.Dp;
+    const int skip = ds.type == T_CATEGORICAL ? 0 : -1;
+    for (int q = lane; q < ds.Dp; q += 32) ((int*)xs_raw)[q] = ds.flag[q] ? src[q] : skip;
+  }
+  __syncwarp();
+  const long long row = (long long)sp.P * sp.N;
+  const int n = ds.n[row];
+  double acc = ds.rc[n];
+  for (int j = 0; j < ds.J; ++j) {
+    double v;
+    if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, n, (const double*)xs_raw, lane);
+    else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)xs_raw, lane);
+    else v = nb_eval_block(ds, row, j, n, (const int*)xs_raw, lane, sp.lf_glob, sp.lf_T);
+    acc += v;
+  }
+  if (lane == 0) *out = acc;
+}
+
+// single-label prefix build used by pmdi_cluster_eval: members -> prototype row 0 of slot P
+__global__ void k_build_one(SweepParams sp, int k, const int* members, int cnt) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  const DsDev& ds = sp.ds[k];
+  if (q >= ds.Dp) return;
+  const long long row = (long long)sp.P * sp.N;
+  build_row_feature(ds, row, q, members, cnt, 1);
+  if (q == 0) ds.n[row] = cnt;
+}
+__global__ void k_aux_one(SweepParams sp, int k) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const DsDev& ds = sp.ds[k];
+  const long long row = (long long)sp.P * sp.N;
+  const int n = ds.n[row];
+  for (int j = w; j < ds.J; j += blockDim.x >> 5) {
+    if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);
+    else if (ds.type == T_NEGBINOM) nb_aux_block(ds, row, j, n, lane, sp.lf_glob, sp.lf_T);
+    else if (lane == 0) ds.aux[row * ds.J + j] = 0.0;
+  }
+}

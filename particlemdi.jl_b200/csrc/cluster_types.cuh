@@ -1,0 +1,256 @@
+// The three built-in cluster types of ParticleMDI as warp-level device operators over one
+// 256-feature block of one cluster row.  Each operator is what the reference's plugin contract
+// computes (calc_logprob / cluster_add!), restructured for HBM streaming:
+//   * everything that does not depend on the observation is hoisted out of the predictive into
+//     aux[row][block] (maintained by the add) and rc[n] (host-built table by cluster size);
+//   * sums of logs become logs of short products (<= 8 factors per lane, no overflow for any
+//     statistic the add can produce), so the FP64 pipe stays far below the HBM time;
+//   * lgamma at integer arguments is a shared-memory log-factorial table.
+// Lane l of a warp owns features {64*it + 2*l, 64*it + 2*l + 1 : it = 0..3} of the block: one
+// 128-bit load per statistic array per iteration, 512 contiguous bytes per warp.
+#pragma once
+#include "device_utils.cuh"
+
+// ------------------------------------------------------------------------------------------
+// Gaussian — reference src/datatypes/gaussian_cluster.jl:37-52 (calc_logprob), :54-66 (cluster_add!)
+//   log p = nflag*rc_n + sum_q flag_q [ 0.5 log(lam_q/(n+1)) - (n/2+1) log(1 + (x_q-mu_q)^2 lam_q/(n+1)) ]
+// stored: mu, lamn = lam/(n+1); aux = sum_q 0.5 log(lamn_q) per block.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double gauss_eval_block(const DsDev& ds, long long row, int j, int n,
+                                                   const double* xs, int lane) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const double* mu = ds.mu + row * ds.Dp + q0 + 2 * lane;
+  const double* lm = ds.lamn + row * ds.Dp + q0 + 2 * lane;
+  double2 m[4], l[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) {
+      m[it] = ldcg_f64x2(mu + it * PMDI_WF);
+      l[it] = ldcg_f64x2(lm + it * PMDI_WF);
+    }
+  double prod = 1.0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) {
+      const double2 x = *(const double2*)(xs + q0 + it * PMDI_WF + 2 * lane);
+      const double d0 = x.x - m[it].x, d1 = x.y - m[it].y;
+      double f0 = fma(d0 * d0, l[it].x, 1.0), f1 = fma(d1 * d1, l[it].y, 1.0);
+      if (!ds.all_on) {
+        const uchar2 fl = *(const uchar2*)(ds.flag + q0 + it * PMDI_WF + 2 * lane);
+        f0 = fl.x ? f0 : 1.0;
+        f1 = fl.y ? f1 : 1.0;
+      }
+      prod *= f0 * f1;
+    }
+  const double s = warp_sum(log(prod));
+  return ldcg_f64(ds.aux + row * ds.J + j) - (0.5 * (double)n + 1.0) * s;
+}
+
+// cluster_add! with the literal operation order of gaussian_cluster.jl:57-63 (no FMA contraction),
+// so the stored statistics carry the same bits as the reference's; n is the size AFTER the add.
+// Returns this lane's share of the new aux (sum of 0.5 log lamn over its flagged features).
+__device__ __forceinline__ void gauss_add_block(const DsDev& ds, long long row, int j, int n,
+                                                const double* xs, int lane) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const double nn = (double)n;
+  const double c1 = __dadd_rn(__dadd_rn(nn, -1.0), 0.001);      // n - 1 + kappa
+  const double c2 = __dmul_rn(2.0, __dadd_rn(nn, 0.001));       // 2 (n + kappa)
+  const double c3 = __dadd_rn(nn, 0.001);                       // n + kappa
+  const double c4 = __dmul_rn(__dadd_rn(__dmul_rn(0.5, nn), 0.5), c3);  // (n/2 + 1/2)(n + kappa)
+  const double c5 = __dadd_rn(nn, 1.001);                       // n + 1 + kappa
+  const double c6 = __dadd_rn(nn, 1.0);
+  const long long base = row * ds.Dp + q0 + 2 * lane;
+  double acc = 0.0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) {
+      const long long o = base + it * PMDI_WF;
+      const double2 x = *(const double2*)(xs + q0 + it * PMDI_WF + 2 * lane);
+      double2 sm = ldcg_f64x2(ds.sum + o), bt = ldcg_f64x2(ds.beta + o), mu = ldcg_f64x2(ds.mu + o);
+      double2 ln = ldcg_f64x2(ds.lamn + o);
+      // padded features carry flag 0: they must not enter aux
+      const uchar2 fl = *(const uchar2*)(ds.flag + q0 + it * PMDI_WF + 2 * lane);
+      if (fl.x) {
+        sm.x = __dadd_rn(sm.x, x.x);
+        const double dd = __dadd_rn(x.x, -mu.x);
+        bt.x = __dadd_rn(bt.x, __ddiv_rn(__dmul_rn(c1, __dmul_rn(dd, dd)), c2));
+        mu.x = __ddiv_rn(sm.x, c3);
+        ln.x = __ddiv_rn(__ddiv_rn(c4, __dmul_rn(bt.x, c5)), c6);
+        acc += 0.5 * log(ln.x);
+      }
+      if (fl.y) {
+        sm.y = __dadd_rn(sm.y, x.y);
+        const double dd = __dadd_rn(x.y, -mu.y);
+        bt.y = __dadd_rn(bt.y, __ddiv_rn(__dmul_rn(c1, __dmul_rn(dd, dd)), c2));
+        mu.y = __ddiv_rn(sm.y, c3);
+        ln.y = __ddiv_rn(__ddiv_rn(c4, __dmul_rn(bt.y, c5)), c6);
+        acc += 0.5 * log(ln.y);
+      }
+      *(double2*)(ds.sum + o) = sm;
+      *(double2*)(ds.beta + o) = bt;
+      *(double2*)(ds.mu + o) = mu;
+      *(double2*)(ds.lamn + o) = ln;
+    }
+  acc = warp_sum(acc);
+  if (lane == 0) ds.aux[row * ds.J + j] = acc;
+}
+
+// aux of a row from its stored state (used after the prefix build)
+__device__ __forceinline__ void gauss_aux_block(const DsDev& ds, long long row, int j, int lane) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  double acc = 0.0;
+  for (int it = 0; it < nit; ++it) {
+    const int q = q0 + it * PMDI_WF + 2 * lane;
+    const double2 ln = *(const double2*)(ds.lamn + row * ds.Dp + q);
+    if (ds.flag[q]) acc += 0.5 * log(ln.x);
+    if (ds.flag[q + 1]) acc += 0.5 * log(ln.y);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ds.aux[row * ds.J + j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Categorical — reference src/datatypes/categorical_cluster.jl:29-41, :43-51
+//   log p = -sum_q flag_q log(nlevels_q + n)  [rc_n]  + sum_q flag_q log(0.5 + counts[x_q, q])
+// The staged observation holds level 0 for unflagged / padded features.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double cat_eval_block(const DsDev& ds, long long row, int j,
+                                                 const int* xs, int lane) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const uint32_t* cnt = ds.cnt + row * (long long)ds.Lmax * ds.Dp;
+  unsigned c[8];
+  int2 lv[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) {
+      const int q = q0 + it * PMDI_WF + 2 * lane;
+      lv[it] = *(const int2*)(xs + q);
+      c[2 * it] = lv[it].x ? ldcg_u32(cnt + (long long)(lv[it].x - 1) * ds.Dp + q) : 0u;
+      c[2 * it + 1] = lv[it].y ? ldcg_u32(cnt + (long long)(lv[it].y - 1) * ds.Dp + q + 1) : 0u;
+    }
+  double prod = 1.0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) {
+      const double f0 = lv[it].x ? 0.5 + (double)c[2 * it] : 1.0;
+      const double f1 = lv[it].y ? 0.5 + (double)c[2 * it + 1] : 1.0;
+      prod *= f0 * f1;
+    }
+  return warp_sum(log(prod));
+}
+
+__device__ __forceinline__ void cat_add_block(const DsDev& ds, long long row, int j, const int* xs,
+                                              int lane) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  uint32_t* cnt = ds.cnt + row * (long long)ds.Lmax * ds.Dp;
+  for (int it = 0; it < nit; ++it) {
+    const int q = q0 + it * PMDI_WF + 2 * lane;
+    const int2 lv = *(const int2*)(xs + q);
+    if (lv.x) { uint32_t* p = cnt + (long long)(lv.x - 1) * ds.Dp + q; *p = ldcg_u32(p) + 1u; }
+    if (lv.y) { uint32_t* p = cnt + (long long)(lv.y - 1) * ds.Dp + q + 1; *p = ldcg_u32(p) + 1u; }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// NegBinom — reference src/datatypes/negbinom_cluster.jl:22-41, :43-51.  All lgamma arguments
+// are integers (lf(k) = lgamma(k+1)):
+//   term_q = lf(n+1) - lf(n) + [lf(n+1+S_q) - lf(S_q)] + [lf(x_q+S_q) - lf(n+2+x_q+S_q)]
+//            \_ rc_n (nflag log(n+1)) _/ \________ aux ________/ \___ per observation ___/
+// The staged observation holds -1 for unflagged / padded features.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double nb_eval_block(const DsDev& ds, long long row, int j, int n,
+                                                const int* xs, int lane, const double* lf, int T) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const long long* S = ds.S + row * ds.Dp + q0 + 2 * lane;
+  longlong2 s[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) s[it] = ldcg_i64x2(S + it * PMDI_WF);
+  double acc = 0.0;
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) {
+      const int2 x = *(const int2*)(xs + q0 + it * PMDI_WF + 2 * lane);
+      if (x.x >= 0) { const long long a = s[it].x + x.x; acc += lfact(a, lf, T) - lfact(a + n + 2, lf, T); }
+      if (x.y >= 0) { const long long a = s[it].y + x.y; acc += lfact(a, lf, T) - lfact(a + n + 2, lf, T); }
+    }
+  return ldcg_f64(ds.aux + row * ds.J + j) + warp_sum(acc);
+}
+
+// n is the size AFTER the add
+__device__ __forceinline__ void nb_add_block(const DsDev& ds, long long row, int j, int n,
+                                             const int* xs, int lane, const double* lf, int T) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  long long* S = ds.S + row * ds.Dp + q0 + 2 * lane;
+  double acc = 0.0;
+  for (int it = 0; it < nit; ++it) {
+    const int2 x = *(const int2*)(xs + q0 + it * PMDI_WF + 2 * lane);
+    longlong2 s = ldcg_i64x2(S + it * PMDI_WF);
+    if (x.x >= 0) { s.x += x.x; acc += lfact(s.x + n + 1, lf, T) - lfact(s.x, lf, T); }
+    if (x.y >= 0) { s.y += x.y; acc += lfact(s.y + n + 1, lf, T) - lfact(s.y, lf, T); }
+    *(longlong2*)(S + it * PMDI_WF) = s;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ds.aux[row * ds.J + j] = acc;
+}
+
+__device__ __forceinline__ void nb_aux_block(const DsDev& ds, long long row, int j, int n, int lane,
+                                             const double* lf, int T) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  double acc = 0.0;
+  for (int it = 0; it < nit; ++it) {
+    const int q = q0 + it * PMDI_WF + 2 * lane;
+    const longlong2 s = *(const longlong2*)(ds.S + row * ds.Dp + q);
+    if (ds.flag[q]) acc += lfact(s.x + n + 1, lf, T) - lfact(s.x, lf, T);
+    if (ds.flag[q + 1]) acc += lfact(s.y + n + 1, lf, T) - lfact(s.y, lf, T);
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) ds.aux[row * ds.J + j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Row movement for resampling (src/pmdi.jl:318-341 in dense form): one warp moves one cluster
+// row src -> dst, or resets dst to the empty state when the source label is empty.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void row_copy(const DsDev& ds, long long src, long long dst, int lane) {
+  const int ns = ldcg_i32(ds.n + src), nd = ldcg_i32(ds.n + dst);
+  if (ns == 0 && nd == 0) return;
+  const int Dp = ds.Dp;
+  if (ds.type == T_GAUSSIAN) {
+    for (int q = 2 * lane; q < Dp; q += 64) {
+      double2 a, b, c, d;
+      if (ns) {
+        a = ldcg_f64x2(ds.mu + src * Dp + q); b = ldcg_f64x2(ds.lamn + src * Dp + q);
+        c = ldcg_f64x2(ds.sum + src * Dp + q); d = ldcg_f64x2(ds.beta + src * Dp + q);
+      } else {
+        a = make_double2(0.0, 0.0); b = make_double2(1.0, 1.0);
+        c = make_double2(0.0, 0.0); d = make_double2(0.5, 0.5);
+      }
+      *(double2*)(ds.mu + dst * Dp + q) = a; *(double2*)(ds.lamn + dst * Dp + q) = b;
+      *(double2*)(ds.sum + dst * Dp + q) = c; *(double2*)(ds.beta + dst * Dp + q) = d;
+    }
+  } else if (ds.type == T_CATEGORICAL) {
+    const long long W = (long long)ds.Lmax * Dp;
+    for (long long q = 4 * lane; q < W; q += 128) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ns) v = __ldcg((const uint4*)(ds.cnt + src * W + q));
+      *(uint4*)(ds.cnt + dst * W + q) = v;
+    }
+  } else {
+    for (int q = 2 * lane; q < Dp; q += 64) {
+      longlong2 v = make_longlong2(0, 0);
+      if (ns) v = ldcg_i64x2(ds.S + src * Dp + q);
+      *(longlong2*)(ds.S + dst * Dp + q) = v;
+    }
+  }
+  for (int j = lane; j < ds.J; j += 32) ds.aux[dst * ds.J + j] = ns ? ldcg_f64(ds.aux + src * ds.J + j) : 0.0;
+  if (lane == 0) ds.n[dst] = ns;
+}

@@ -1,0 +1,749 @@
+// libpmdi_cuda.so — host side of the C-ABI declared in include/pmdi_cuda.h.
+// Owns device memory, builds the x-independent tables, assigns (dataset, particle) units to CTAs
+// and launches the kernels.  No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/pmdi_cuda.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <queue>
+#include <string>
+#include <vector>
+
+#include "aux_kernels.cuh"
+#include "sweep_kernel.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CK(call)                                                                            \
+  do {                                                                                      \
+    cudaError_t e_ = (call);                                                                \
+    if (e_ != cudaSuccess)                                                                  \
+      return fail(100 + (int)e_, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+  } while (0)
+
+template <class T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t n) {
+    if (n <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
+    if (e == cudaSuccess) cap = n;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct Dataset {
+  bool bound = false;
+  int type = -1, D = 0, Dp = 0, J = 0, Lmax = 0;
+  long long max_arg = 0;               // NegBinom: largest lgamma argument the sweep can form
+  std::vector<uint8_t> flag;           // [Dp]
+  std::vector<double> nlevels;         // categorical [D]
+  bool rc_dirty = true;
+  DevBuf<unsigned char> x;
+  DevBuf<uint8_t> d_flag;
+  DevBuf<double> rc, d_nlevels;
+  DevBuf<double> mu, lamn, sum, beta, part, aux;
+  DevBuf<uint32_t> cnt;
+  DevBuf<long long> S;
+  DevBuf<int> n;
+  void release() {
+    x.release(); d_flag.release(); rc.release(); d_nlevels.release();
+    mu.release(); lamn.release(); sum.release(); beta.release(); part.release(); aux.release();
+    cnt.release(); S.release(); n.release();
+  }
+};
+
+}  // namespace
+
+struct pmdi_ctx {
+  int K = 0, N = 0, P = 0, device = 0;
+  long long n = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n_sm = 0, G = 0;
+  std::vector<Dataset> ds;
+  bool layout_dirty = true;
+  // static layout
+  std::vector<int> cta_off, cta_units;
+  int max_units = 0, sm_x_bytes = 0, lf_T = 0, sm_rowcap = 0, Jmax = 0;
+  size_t dyn_smem = 0;
+  std::vector<double> lf_host;
+  DevBuf<double> lf_dev;
+  DevBuf<int> d_cta_off, d_cta_units;
+  // per-sweep inputs
+  DevBuf<double> Pi, l1phi, tape_alloc, tape_resamp, tape_shuffle, tape_select;
+  DevBuf<long long> s_in, s_out, d_pstar, cluster_n, counters;
+  DevBuf<int> order, slot_of, anc_log, ev_of_step, members, mem_off, cur_at, plan_out, err;
+  DevBuf<int> sc_j, sc_anc0, sc_a, sc_b, sc_c, sc_d;
+  DevBuf<double> lw, lw_out, sc_w, sc_pp, sc_u;
+  DevBuf<uint8_t> lab, alloc_log;
+  DevBuf<int2> copies;
+  DevBuf<unsigned> bar;
+  DevBuf<unsigned long long> rows_eval, phase_ns;
+  DevBuf<double> dbg_lp, dbg_lw, scratch_d;
+  DevBuf<int> dbg_alloc, dbg_anc, scratch_i;
+  DevBuf<uint8_t> scratch_u8;
+  SweepParams sp;
+  bool uploaded = false, ran = false;
+  unsigned sweep_flags = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
+};
+
+namespace {
+
+int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+void fill_dsdev(pmdi_ctx* c, int k, DsDev& d) {
+  Dataset& s = c->ds[k];
+  std::memset(&d, 0, sizeof(d));
+  d.type = s.type; d.D = s.D; d.Dp = s.Dp; d.J = s.J; d.Lmax = s.Lmax;
+  int nflag = 0;
+  for (int q = 0; q < s.D; ++q) nflag += s.flag[q] ? 1 : 0;
+  d.nflag = nflag;
+  d.all_on = (nflag == s.D && s.D == s.Dp) ? 1 : 0;
+  // padded Gaussian features evaluate to a factor of exactly 1 without the flag test
+  if (s.type == T_GAUSSIAN && nflag == s.D) d.all_on = 1;
+  d.x = s.x.p; d.flag = s.d_flag.p; d.rc = s.rc.p;
+  d.mu = s.mu.p; d.lamn = s.lamn.p; d.sum = s.sum.p; d.beta = s.beta.p;
+  d.cnt = s.cnt.p; d.S = s.S.p; d.part = s.part.p; d.aux = s.aux.p; d.n = s.n.p;
+}
+
+// x-independent row constants by cluster size n:
+//  Gaussian    nflag * (log(1/sqrt(pi)) + lgamma(n/2+1) - lgamma(n/2+1/2))   gaussian_cluster.jl:38-40
+//  Categorical -sum_q flag_q log(nlevels_q + n)                              categorical_cluster.jl:30
+//  NegBinom    nflag * (lgamma(n+2) - lgamma(n+1)) = nflag log(n+1)          negbinom_cluster.jl:33,37
+int build_rc(pmdi_ctx* c, int k) {
+  Dataset& s = c->ds[k];
+  const long long n = c->n;
+  std::vector<double> rc(n + 1);
+  int nflag = 0;
+  for (int q = 0; q < s.D; ++q) nflag += s.flag[q] ? 1 : 0;
+  if (s.type == T_GAUSSIAN) {
+    for (long long i = 0; i <= n; ++i) {
+      const double nn = (double)i;
+      rc[i] = nflag * (std::log(1.0 / std::sqrt(M_PI)) + std::lgamma(0.5 * nn + 1.0) -
+                       std::lgamma(0.5 * nn + 0.5));
+    }
+  } else if (s.type == T_CATEGORICAL) {
+    std::map<double, long long> hist;
+    for (int q = 0; q < s.D; ++q)
+      if (s.flag[q]) hist[s.nlevels[q]] += 1;
+    for (long long i = 0; i <= n; ++i) {
+      double acc = 0.0;
+      for (auto& kv : hist) acc += (double)kv.second * std::log(kv.first + (double)i);
+      rc[i] = -acc;
+    }
+  } else {
+    for (long long i = 0; i <= n; ++i) rc[i] = nflag * std::log((double)i + 1.0);
+  }
+  CK(s.rc.ensure(n + 1));
+  CK(cudaMemcpyAsync(s.rc.p, rc.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  s.rc_dirty = false;
+  return 0;
+}
+
+// Static layout: shared-memory budget, log-factorial table, units -> CTAs (longest-processing-time
+// greedy on bytes per occupied row, so every CTA streams a similar number of bytes per step).
+int build_layout(pmdi_ctx* c) {
+  const int K = c->K, P = c->P, N = c->N;
+  for (int k = 0; k < K; ++k)
+    if (!c->ds[k].bound) return fail(3, "pmdi: dataset " + std::to_string(k) + " is not bound");
+  int off = 0, Jmax = 1;
+  long long nb_max_arg = -1;
+  for (int k = 0; k < K; ++k) {
+    Dataset& s = c->ds[k];
+    off = round_up(off, 16);
+    c->sp.ds[k].x_off = off;  // re-applied in fill (see below)
+    off += s.Dp * (s.type == T_GAUSSIAN ? 8 : 4);
+    Jmax = std::max(Jmax, s.J);
+    if (s.type == T_NEGBINOM) nb_max_arg = std::max(nb_max_arg, s.max_arg);
+  }
+  c->sm_x_bytes = round_up(off, 16);
+  c->Jmax = Jmax;
+  // units
+  struct U { double cost; int k, slot; };
+  std::vector<U> units;
+  for (int k = 0; k < K; ++k) {
+    const Dataset& s = c->ds[k];
+    const double w = s.type == T_GAUSSIAN ? 16.0 : (s.type == T_NEGBINOM ? 8.0 : 4.0);
+    for (int p = 0; p < P; ++p) units.push_back({w * s.Dp + 64.0, k, p});
+    units.push_back({(w * s.Dp + 64.0) * 0.25, k, P + 1});
+  }
+  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
+  const int G = c->G;
+  typedef std::pair<double, int> QE;
+  std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
+  for (int g = 0; g < G; ++g) pq.push({0.0, g});
+  std::vector<std::vector<int>> per(G);
+  for (const U& u : units) {
+    QE top = pq.top();
+    pq.pop();
+    per[top.second].push_back((u.k << 24) | u.slot);
+    pq.push({top.first + u.cost, top.second});
+  }
+  c->cta_off.assign(G + 1, 0);
+  c->cta_units.clear();
+  c->max_units = 1;
+  for (int g = 0; g < G; ++g) {
+    c->cta_off[g] = (int)c->cta_units.size();
+    c->cta_units.insert(c->cta_units.end(), per[g].begin(), per[g].end());
+    c->max_units = std::max(c->max_units, (int)per[g].size());
+  }
+  c->cta_off[G] = (int)c->cta_units.size();
+  c->sm_rowcap = c->max_units * N;
+  // log-factorial table in shared memory (NegBinom only)
+  int dev_smem = 0;
+  CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
+  const long long budget = (long long)dev_smem - 8192 - c->sm_x_bytes - (long long)c->sm_rowcap * 4;
+  if (budget < 0) return fail(4, "pmdi: datasets too wide for the shared-memory observation staging");
+  c->lf_T = 0;
+  if (nb_max_arg >= 0) {
+    const long long want = nb_max_arg + 2, cap = budget / 8;
+    if (cap < 256) return fail(4, "pmdi: no shared memory left for the log-factorial table");
+    c->lf_T = (int)std::min(want, cap);
+    if (c->lf_T < 256) c->lf_T = 256;
+    c->lf_host.resize(c->lf_T);
+    for (int i = 0; i < c->lf_T; ++i) c->lf_host[i] = std::lgamma((double)i + 1.0);
+    CK(c->lf_dev.ensure(c->lf_T));
+    CK(cudaMemcpy(c->lf_dev.p, c->lf_host.data(), sizeof(double) * c->lf_T, cudaMemcpyHostToDevice));
+  }
+  c->dyn_smem = (size_t)c->sm_x_bytes + (size_t)c->lf_T * 8 + (size_t)c->sm_rowcap * 4;
+  CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+  CK(c->d_cta_off.ensure(c->cta_off.size()));
+  CK(c->d_cta_units.ensure(c->cta_units.size()));
+  CK(cudaMemcpy(c->d_cta_off.p, c->cta_off.data(), sizeof(int) * c->cta_off.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_cta_units.p, c->cta_units.data(), sizeof(int) * c->cta_units.size(), cudaMemcpyHostToDevice));
+  c->layout_dirty = false;
+  return 0;
+}
+
+int fill_params(pmdi_ctx* c) {
+  SweepParams& sp = c->sp;
+  int off = 0;
+  for (int k = 0; k < c->K; ++k) {
+    fill_dsdev(c, k, sp.ds[k]);
+    off = round_up(off, 16);
+    sp.ds[k].x_off = off;
+    off += c->ds[k].Dp * (c->ds[k].type == T_GAUSSIAN ? 8 : 4);
+  }
+  sp.K = c->K; sp.N = c->N; sp.P = c->P; sp.n_obs = (int)c->n; sp.G = c->G;
+  sp.Jmax = c->Jmax;
+  sp.cta_off = c->d_cta_off.p; sp.cta_units = c->d_cta_units.p;
+  sp.max_units = c->max_units; sp.sm_x_bytes = c->sm_x_bytes; sp.lf_T = c->lf_T;
+  sp.sm_rowcap = c->sm_rowcap; sp.lf_glob = c->lf_dev.p;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* pmdi_last_error(void) { return g_err.c_str(); }
+int pmdi_version(void) { return 100; }
+
+int pmdi_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+double pmdi_uniform(uint64_t seed, uint32_t iter, uint32_t kind, uint32_t step, uint32_t k,
+                    uint32_t index) {
+  return pmdi_philox_uniform(seed, iter, kind, step, k, index);
+}
+
+int pmdi_ctx_create(pmdi_ctx** out, int32_t K, int64_t n_obs, int32_t N, int32_t particles,
+                    int32_t device) {
+  if (!out) return fail(1, "pmdi_ctx_create: out is NULL");
+  *out = nullptr;
+  // pre-conditions of pmdi() (src/pmdi.jl:50-55)
+  if (K < 1 || K > PMDI_MAX_K) return fail(1, "pmdi_ctx_create: need 1 <= K <= 8 datasets");
+  if (!(N > 1 && (int64_t)N <= n_obs)) return fail(1, "pmdi_ctx_create: need 1 < N <= n_obs");
+  if (N > PMDI_MAX_N) return fail(1, "pmdi_ctx_create: N > 256 is not supported");
+  if (particles <= 1) return fail(1, "pmdi_ctx_create: need particles > 1");
+  if (n_obs > 0x7fffffff / 2) return fail(1, "pmdi_ctx_create: n_obs too large");
+  if (pmdi_device_count() <= device || device < 0)
+    return fail(2, "pmdi_ctx_create: no CUDA device " + std::to_string(device) +
+                       " (libpmdi_cuda has no CPU fallback)");
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10)
+    return fail(2, "pmdi_ctx_create: built for sm_100a (B200); found compute capability " +
+                       std::to_string(prop.major) + "." + std::to_string(prop.minor));
+  int coop = 0;
+  CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) return fail(2, "pmdi_ctx_create: device lacks cooperative launch");
+  pmdi_ctx* c = new pmdi_ctx();
+  c->K = K; c->n = n_obs; c->N = N; c->P = particles; c->device = device;
+  c->n_sm = prop.multiProcessorCount;
+  c->G = c->n_sm;  // one persistent CTA per SM
+  c->ds.resize(K);
+  std::memset(&c->sp, 0, sizeof(c->sp));
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) { delete c; return fail(100 + (int)e, "cudaStreamCreate failed"); }
+  c->own_stream = true;
+  cudaEventCreate(&c->ev0); cudaEventCreate(&c->ev1); cudaEventCreate(&c->ev2); cudaEventCreate(&c->ev3);
+  *out = c;
+  return 0;
+}
+
+int pmdi_ctx_destroy(pmdi_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (auto& d : c->ds) d.release();
+  DevBuf<double>* dd[] = {&c->lf_dev, &c->Pi, &c->l1phi, &c->tape_alloc, &c->tape_resamp, &c->tape_shuffle,
+                          &c->tape_select, &c->lw, &c->lw_out, &c->sc_w, &c->sc_pp, &c->sc_u, &c->dbg_lp,
+                          &c->dbg_lw, &c->scratch_d};
+  for (auto* b : dd) b->release();
+  DevBuf<int>* di[] = {&c->d_cta_off, &c->d_cta_units, &c->order, &c->slot_of, &c->anc_log, &c->ev_of_step,
+                       &c->members, &c->mem_off, &c->cur_at, &c->plan_out, &c->err, &c->sc_j, &c->sc_anc0,
+                       &c->sc_a, &c->sc_b, &c->sc_c, &c->sc_d, &c->dbg_alloc, &c->dbg_anc, &c->scratch_i};
+  for (auto* b : di) b->release();
+  DevBuf<long long>* dl[] = {&c->s_in, &c->s_out, &c->d_pstar, &c->cluster_n, &c->counters};
+  for (auto* b : dl) b->release();
+  c->lab.release(); c->alloc_log.release(); c->copies.release(); c->bar.release();
+  c->rows_eval.release(); c->phase_ns.release(); c->scratch_u8.release();
+  if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3); }
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int pmdi_ctx_set_stream(pmdi_ctx* c, void* s) {
+  if (!c) return fail(1, "NULL context");
+  if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+  c->stream = (cudaStream_t)s;
+  c->own_stream = false;
+  return 0;
+}
+void* pmdi_ctx_get_stream(pmdi_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int pmdi_set_dataset(pmdi_ctx* c, int32_t k, int32_t type_tag, int32_t elem_kind, const void* data,
+                     int64_t n_obs, int64_t D, int64_t ld) {
+  if (!c) return fail(1, "NULL context");
+  if (k < 0 || k >= c->K) return fail(1, "pmdi_set_dataset: k out of range");
+  if (n_obs != c->n) return fail(1, "pmdi_set_dataset: datasets must have n_obs rows (src/pmdi.jl:52)");
+  if (D < 1 || D > (1 << 20)) return fail(1, "pmdi_set_dataset: bad feature count");
+  if (ld < n_obs) return fail(1, "pmdi_set_dataset: ld < n_obs");
+  if (type_tag < 0 || type_tag > 2) return fail(1, "pmdi_set_dataset: unknown cluster type tag");
+  if ((type_tag == PMDI_GAUSSIAN) != (elem_kind == PMDI_F64))
+    return fail(1, "pmdi_set_dataset: Gaussian needs PMDI_F64 data, Categorical/NegBinom need PMDI_I64");
+  CK(cudaSetDevice(c->device));
+  Dataset& s = c->ds[k];
+  s.release();
+  s.type = type_tag; s.D = (int)D; s.Dp = round_up((int)D, PMDI_WF);
+  s.J = (s.Dp + PMDI_FB - 1) / PMDI_FB;
+  s.Lmax = 0; s.max_arg = 0;
+  const long long n = c->n;
+  const int Dp = s.Dp;
+  s.flag.assign(Dp, 0);
+  for (int q = 0; q < s.D; ++q) s.flag[q] = 1;
+  if (type_tag == PMDI_GAUSSIAN) {
+    std::vector<double> h((size_t)n * Dp, 0.0);
+    const double* x = (const double*)data;
+    for (int q = 0; q < s.D; ++q)
+      for (long long i = 0; i < n; ++i) h[(size_t)i * Dp + q] = x[(size_t)i + (size_t)ld * q];
+    CK(s.x.ensure(h.size() * 8));
+    CK(cudaMemcpy(s.x.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
+  } else {
+    std::vector<int> h((size_t)n * Dp, 0);
+    const int64_t* x = (const int64_t*)data;
+    s.nlevels.assign(s.D, 0.0);
+    long long gmax = 0, max_colsum = 0;
+    for (int q = 0; q < s.D; ++q) {
+      long long cmax = x[(size_t)ld * q], csum = 0;
+      for (long long i = 0; i < n; ++i) {
+        const int64_t v = x[(size_t)i + (size_t)ld * q];
+        if (type_tag == PMDI_CATEGORICAL && v < 1)
+          return fail(1, "pmdi_set_dataset: categorical levels must be >= 1 (use coerce_categorical)");
+        if (type_tag == PMDI_NEGBINOM && v < 0) return fail(1, "pmdi_set_dataset: counts must be >= 0");
+        if (v > 0x3fffffff) return fail(1, "pmdi_set_dataset: value too large");
+        h[(size_t)i * Dp + q] = (int)v;
+        cmax = std::max<long long>(cmax, v);
+        csum += v;
+      }
+      s.nlevels[q] = 0.5 * (double)cmax;  // categorical_cluster.jl:10
+      gmax = std::max(gmax, cmax);
+      max_colsum = std::max(max_colsum, csum);
+    }
+    if (type_tag == PMDI_CATEGORICAL) {
+      if (gmax > 4096) return fail(1, "pmdi_set_dataset: more than 4096 categorical levels");
+      s.Lmax = (int)gmax;  // categorical_cluster.jl:8
+      CK(s.d_nlevels.ensure(s.D));
+      CK(cudaMemcpy(s.d_nlevels.p, s.nlevels.data(), sizeof(double) * s.D, cudaMemcpyHostToDevice));
+    } else {
+      s.max_arg = max_colsum + n + 3;
+    }
+    CK(s.x.ensure(h.size() * 4));
+    CK(cudaMemcpy(s.x.p, h.data(), h.size() * 4, cudaMemcpyHostToDevice));
+  }
+  CK(s.d_flag.ensure(Dp));
+  CK(cudaMemcpy(s.d_flag.p, s.flag.data(), Dp, cudaMemcpyHostToDevice));
+  const long long rows = (long long)(c->P + 2) * c->N;
+  if (type_tag == PMDI_GAUSSIAN) {
+    CK(s.mu.ensure(rows * Dp)); CK(s.lamn.ensure(rows * Dp));
+    CK(s.sum.ensure(rows * Dp)); CK(s.beta.ensure(rows * Dp));
+  } else if (type_tag == PMDI_CATEGORICAL) {
+    CK(s.cnt.ensure(rows * s.Lmax * Dp));
+  } else {
+    CK(s.S.ensure(rows * Dp));
+  }
+  CK(s.part.ensure(rows * s.J)); CK(s.aux.ensure(rows * s.J)); CK(s.n.ensure(rows));
+  s.bound = true;
+  s.rc_dirty = true;
+  c->layout_dirty = true;
+  DsDev d;
+  fill_dsdev(c, k, d);
+  k_init_rows<<<c->n_sm * 4, 256, 0, c->stream>>>(d, rows);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int pmdi_set_feature_flags(pmdi_ctx* c, int32_t k, const uint8_t* flags) {
+  if (!c) return fail(1, "NULL context");
+  if (k < 0 || k >= c->K || !c->ds[k].bound) return fail(1, "pmdi_set_feature_flags: dataset not bound");
+  CK(cudaSetDevice(c->device));
+  Dataset& s = c->ds[k];
+  for (int q = 0; q < s.D; ++q) s.flag[q] = flags[q] ? 1 : 0;
+  CK(cudaMemcpyAsync(s.d_flag.p, s.flag.data(), s.Dp, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  s.rc_dirty = true;
+  return 0;
+}
+
+static int prepare(pmdi_ctx* c) {
+  CK(cudaSetDevice(c->device));
+  if (c->layout_dirty) {
+    int rc = build_layout(c);
+    if (rc) return rc;
+  }
+  for (int k = 0; k < c->K; ++k)
+    if (c->ds[k].rc_dirty) {
+      int rc = build_rc(c, k);
+      if (rc) return rc;
+    }
+  return fill_params(c);
+}
+
+int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
+  if (!c || !a) return fail(1, "pmdi_sweep_upload: NULL argument");
+  int rc = prepare(c);
+  if (rc) return rc;
+  const int K = c->K, N = c->N, P = c->P;
+  const long long n = c->n;
+  if (a->n1 < 1 || a->n1 > n) return fail(1, "pmdi_sweep: need 1 <= n1 <= n_obs (n1 = floor(rho*n_obs), src/pmdi.jl:161)");
+  if (!a->s || !a->order_obs || !a->Pi) return fail(1, "pmdi_sweep: s, order_obs and Pi are required");
+  if (K > 1 && !a->phi) return fail(1, "pmdi_sweep: phi is required when K > 1");
+  const int steps = (int)(n - a->n1 + 1);
+  SweepParams& sp = c->sp;
+  // validate + convert
+  std::vector<int> order(n);
+  std::vector<uint8_t> seen(n, 0);
+  for (long long i = 0; i < n; ++i) {
+    const int64_t o = a->order_obs[i];
+    if (o < 1 || o > n || seen[o - 1]) return fail(1, "pmdi_sweep: order_obs is not a permutation of 1..n_obs");
+    seen[o - 1] = 1;
+    order[i] = (int)(o - 1);
+  }
+  for (long long i = 0; i < n * K; ++i)
+    if (a->s[i] < 1 || a->s[i] > N) return fail(1, "pmdi_sweep: allocation label outside 1..N");
+  const int npairs = K * (K - 1) / 2;
+  std::vector<double> l1phi(std::max(npairs, 1), 0.0);
+  for (int i = 0; i < npairs; ++i) l1phi[i] = std::log(1 + a->phi[i]);  // src/misc.jl:53
+  cudaStream_t st = c->stream;
+  CK(c->s_in.ensure(n * K)); CK(c->s_out.ensure(n * K)); CK(c->order.ensure(n));
+  CK(c->Pi.ensure((size_t)N * K)); CK(c->l1phi.ensure(l1phi.size()));
+  CK(cudaMemcpyAsync(c->s_in.p, a->s, sizeof(int64_t) * n * K, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->order.p, order.data(), sizeof(int) * n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->Pi.p, a->Pi, sizeof(double) * N * K, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->l1phi.p, l1phi.data(), sizeof(double) * l1phi.size(), cudaMemcpyHostToDevice, st));
+  sp.tape_alloc = sp.tape_resamp = sp.tape_shuffle = sp.tape_select = nullptr;
+  if (a->tape_alloc) {
+    CK(c->tape_alloc.ensure((size_t)steps * K * P));
+    CK(cudaMemcpyAsync(c->tape_alloc.p, a->tape_alloc, sizeof(double) * steps * K * P, cudaMemcpyHostToDevice, st));
+    sp.tape_alloc = c->tape_alloc.p;
+  }
+  if (a->tape_resamp) {
+    CK(c->tape_resamp.ensure(steps));
+    CK(cudaMemcpyAsync(c->tape_resamp.p, a->tape_resamp, sizeof(double) * steps, cudaMemcpyHostToDevice, st));
+    sp.tape_resamp = c->tape_resamp.p;
+  }
+  if (a->tape_shuffle) {
+    CK(c->tape_shuffle.ensure((size_t)steps * P));
+    CK(cudaMemcpyAsync(c->tape_shuffle.p, a->tape_shuffle, sizeof(double) * steps * P, cudaMemcpyHostToDevice, st));
+    sp.tape_shuffle = c->tape_shuffle.p;
+  }
+  if (a->tape_select) {
+    CK(c->tape_select.ensure(1));
+    CK(cudaMemcpyAsync(c->tape_select.p, a->tape_select, sizeof(double), cudaMemcpyHostToDevice, st));
+    sp.tape_select = c->tape_select.p;
+  }
+  // state buffers
+  CK(c->lw.ensure(P)); CK(c->lw_out.ensure(P)); CK(c->slot_of.ensure(2 * (size_t)P));
+  CK(c->lab.ensure((size_t)K * P)); CK(c->alloc_log.ensure((size_t)steps * K * P));
+  CK(c->anc_log.ensure((size_t)steps * P)); CK(c->ev_of_step.ensure(steps));
+  CK(c->sc_w.ensure(P)); CK(c->sc_pp.ensure(P)); CK(c->sc_u.ensure(P));
+  CK(c->sc_j.ensure(P)); CK(c->sc_anc0.ensure(P)); CK(c->sc_a.ensure(P)); CK(c->sc_b.ensure(P));
+  CK(c->sc_c.ensure(P)); CK(c->sc_d.ensure(P)); CK(c->copies.ensure(P)); CK(c->plan_out.ensure(4));
+  CK(c->bar.ensure(4)); CK(c->err.ensure(4)); CK(c->rows_eval.ensure(PMDI_MAX_K)); CK(c->counters.ensure(4));
+  CK(c->phase_ns.ensure(8)); CK(c->d_pstar.ensure(1)); CK(c->cluster_n.ensure((size_t)K * P * N));
+  CK(c->members.ensure((size_t)K * std::max<long long>(a->n1 - 1, 1))); CK(c->mem_off.ensure((size_t)K * (N + 1)));
+  CK(c->cur_at.ensure(steps));
+  sp.n1 = (int)a->n1; sp.steps = steps; sp.flags = (int)a->flags;
+  sp.Pi = c->Pi.p; sp.l1phi = c->l1phi.p; sp.s_in = c->s_in.p; sp.order = c->order.p;
+  sp.lw_init = a->logweight_init; sp.seed = a->seed; sp.iter = a->iter;
+  sp.lw = c->lw.p; sp.slot_of = c->slot_of.p; sp.lab = c->lab.p; sp.alloc_log = c->alloc_log.p;
+  sp.anc_log = c->anc_log.p; sp.ev_of_step = c->ev_of_step.p;
+  sp.sc_w = c->sc_w.p; sp.sc_pp = c->sc_pp.p; sp.sc_u = c->sc_u.p; sp.sc_j = c->sc_j.p;
+  sp.sc_anc0 = c->sc_anc0.p; sp.sc_a = c->sc_a.p; sp.sc_b = c->sc_b.p; sp.sc_c = c->sc_c.p;
+  sp.sc_d = c->sc_d.p; sp.copies = c->copies.p; sp.plan_out = c->plan_out.p;
+  sp.bar = c->bar.p; sp.err = c->err.p; sp.rows_eval = c->rows_eval.p; sp.counters = c->counters.p;
+  sp.phase_ns = (a->flags & PMDI_SWEEP_TIME_PHASES) ? c->phase_ns.p : nullptr;
+  sp.dbg_lp = nullptr; sp.dbg_lw = nullptr; sp.dbg_alloc = nullptr; sp.dbg_anc = nullptr;
+  if (a->flags & PMDI_SWEEP_DEBUG) {
+    CK(c->dbg_lp.ensure((size_t)steps * K * P * N)); CK(c->dbg_lw.ensure((size_t)steps * P));
+    CK(c->dbg_alloc.ensure((size_t)steps * K * P)); CK(c->dbg_anc.ensure((size_t)steps * P));
+    CK(cudaMemsetAsync(c->dbg_anc.p, 0, sizeof(int) * (size_t)steps * P, st));
+    sp.dbg_lp = c->dbg_lp.p; sp.dbg_lw = c->dbg_lw.p; sp.dbg_alloc = c->dbg_alloc.p; sp.dbg_anc = c->dbg_anc.p;
+  }
+  CK(cudaMemsetAsync(c->phase_ns.p, 0, 64, st));
+  c->sweep_flags = a->flags;
+  c->uploaded = true;
+  c->ran = false;
+  // pageable host sources: make the call safe to return from
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pmdi_sweep_run(pmdi_ctx* c) {
+  if (!c || !c->uploaded) return fail(1, "pmdi_sweep_run: call pmdi_sweep_upload first");
+  CK(cudaSetDevice(c->device));
+  const SweepParams& sp = c->sp;
+  cudaStream_t st = c->stream;
+  const int K = c->K, N = c->N, P = c->P;
+  CK(cudaEventRecord(c->ev0, st));
+  k_sweep_init<<<(P + 255) / 256, 256, 0, st>>>(sp);
+  if (sp.n1 > 1) {
+    k_prefix_lists<<<K, PMDI_MAX_N + 32, 0, st>>>(sp, c->members.p, c->mem_off.p);
+  } else {
+    CK(cudaMemsetAsync(c->mem_off.p, 0, sizeof(int) * K * (N + 1), st));
+  }
+  int maxDp = 0;
+  for (int k = 0; k < K; ++k) maxDp = std::max(maxDp, c->ds[k].Dp);
+  k_prefix_build<<<dim3((maxDp + 127) / 128, N, K), 128, 0, st>>>(sp, c->members.p, c->mem_off.p);
+  k_proto_aux<<<dim3(N, K), 256, 0, st>>>(sp);
+  k_broadcast<<<c->n_sm * 8, 256, 0, st>>>(sp);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev1, st));
+  void* args[] = {(void*)&c->sp};
+  CK(cudaLaunchCooperativeKernel((const void*)k_sweep, dim3(c->G), dim3(PMDI_NT), args, c->dyn_smem, st));
+  CK(cudaEventRecord(c->ev2, st));
+  k_finish<<<1, 256, 0, st>>>(sp, (c->sweep_flags & PMDI_SWEEP_SSTAR_COMPAT) ? 1 : 0, c->s_out.p, c->d_pstar.p,
+                              c->lw_out.p, c->cluster_n.p, c->cur_at.p);
+  CK(cudaGetLastError());
+  CK(cudaEventRecord(c->ev3, st));
+  c->ran = true;
+  return 0;
+}
+
+int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
+  if (!c || !o || !c->ran) return fail(1, "pmdi_sweep_download: call pmdi_sweep_run first");
+  CK(cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int K = c->K, N = c->N, P = c->P;
+  const long long n = c->n;
+  const int steps = c->sp.steps;
+  int err = 0;
+  long long counters[4] = {0, 0, 0, 0};
+  unsigned long long rows[PMDI_MAX_K], phase[8];
+  long long pstar = 0;
+  CK(cudaMemcpyAsync(&err, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(counters, c->counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(rows, c->rows_eval.p, sizeof(rows), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(phase, c->phase_ns.p, sizeof(phase), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(&pstar, c->d_pstar.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
+  if (o->s) CK(cudaMemcpyAsync(o->s, c->s_out.p, sizeof(int64_t) * n * K, cudaMemcpyDeviceToHost, st));
+  if (o->logweight) CK(cudaMemcpyAsync(o->logweight, c->lw_out.p, sizeof(double) * P, cudaMemcpyDeviceToHost, st));
+  if (o->cluster_n)
+    CK(cudaMemcpyAsync(o->cluster_n, c->cluster_n.p, sizeof(int64_t) * K * P * N, cudaMemcpyDeviceToHost, st));
+  if (c->sweep_flags & PMDI_SWEEP_DEBUG) {
+    if (o->dbg_lp) CK(cudaMemcpyAsync(o->dbg_lp, c->dbg_lp.p, sizeof(double) * (size_t)steps * K * P * N, cudaMemcpyDeviceToHost, st));
+    if (o->dbg_lw) CK(cudaMemcpyAsync(o->dbg_lw, c->dbg_lw.p, sizeof(double) * (size_t)steps * P, cudaMemcpyDeviceToHost, st));
+    if (o->dbg_alloc) CK(cudaMemcpyAsync(o->dbg_alloc, c->dbg_alloc.p, sizeof(int) * (size_t)steps * K * P, cudaMemcpyDeviceToHost, st));
+    if (o->dbg_anc) CK(cudaMemcpyAsync(o->dbg_anc, c->dbg_anc.p, sizeof(int) * (size_t)steps * P, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  if (err != 0)
+    return fail(50 + err, err == 77 ? "pmdi_sweep: grid barrier watchdog fired (a CTA did not arrive)"
+                                    : "pmdi_sweep: device-side error " + std::to_string(err));
+  if (o->p_star) *o->p_star = pstar;
+  o->n_resamples = counters[0];
+  o->n_copies = counters[1];
+  long long ev = 0, dense = 0;
+  for (int k = 0; k < K; ++k) {
+    ev += (long long)rows[k] * c->ds[k].D;
+    dense += (long long)steps * P * N * c->ds[k].D;
+    o->rows_evaluated[k] = (int64_t)rows[k];
+  }
+  for (int k = K; k < 8; ++k) o->rows_evaluated[k] = 0;
+  o->n_evals = ev;
+  o->n_evals_dense = dense;
+  float ms = 0.f;
+  CK(cudaEventElapsedTime(&ms, c->ev0, c->ev3));
+  o->device_ms = ms;
+  CK(cudaEventElapsedTime(&ms, c->ev1, c->ev2));
+  o->sweep_kernel_ms = ms;
+  for (int i = 0; i < 6; ++i) o->phase_ms[i] = (double)phase[i] * 1e-6;
+  return 0;
+}
+
+int pmdi_sweep(pmdi_ctx* c, const pmdi_sweep_args* a, pmdi_sweep_out* o) {
+  int rc = pmdi_sweep_upload(c, a);
+  if (rc) return rc;
+  rc = pmdi_sweep_run(c);
+  if (rc) return rc;
+  return pmdi_sweep_download(c, o);
+}
+
+// ---------------------------------------------------------------------------------------------
+// feature selection and single-cluster evaluation
+// ---------------------------------------------------------------------------------------------
+static double gauss_marginal_cst(double n) {  // gaussian_cluster.jl:71-82
+  const double a_n = n / 2 + 0.5, a_0 = 0.5, b_0 = 0.5, k_0 = 0.001, k_n = n + k_0;
+  return (a_0 * std::log(b_0)) + std::lgamma(a_n) - std::lgamma(a_0) +
+         0.5 * (std::log(k_0) - std::log(k_n)) - (n * 0.5) * std::log(2 * M_PI);
+}
+
+static int run_logmarginal(pmdi_ctx* c, int k, const std::vector<int>& off, const std::vector<int>& mem,
+                           int use_flags, const double* base_host, double base_scale, double out_scale,
+                           double* out_host, uint8_t* flags_host, const double* tape_f, uint64_t seed,
+                           uint32_t iter) {
+  Dataset& s = c->ds[k];
+  const int nc = (int)off.size() - 1, D = s.D;
+  std::vector<double> cst(std::max(nc, 1));
+  for (int i = 0; i < nc; ++i) cst[i] = gauss_marginal_cst((double)(off[i + 1] - off[i]));
+  cudaStream_t st = c->stream;
+  CK(c->scratch_i.ensure(off.size() + mem.size() + 1));
+  CK(c->scratch_d.ensure((size_t)nc + 1 + 3 * (size_t)D));
+  CK(c->scratch_u8.ensure(D));
+  int* d_off = c->scratch_i.p;
+  int* d_mem = c->scratch_i.p + off.size();
+  double* d_cst = c->scratch_d.p;
+  double* d_base = d_cst + nc + 1;
+  double* d_out = d_base + D;
+  double* d_tape = d_out + D;
+  CK(cudaMemcpyAsync(d_off, off.data(), sizeof(int) * off.size(), cudaMemcpyHostToDevice, st));
+  if (!mem.empty()) CK(cudaMemcpyAsync(d_mem, mem.data(), sizeof(int) * mem.size(), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d_cst, cst.data(), sizeof(double) * cst.size(), cudaMemcpyHostToDevice, st));
+  if (base_host) CK(cudaMemcpyAsync(d_base, base_host, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+  if (tape_f) CK(cudaMemcpyAsync(d_tape, tape_f, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+  DsDev d;
+  fill_dsdev(c, k, d);
+  k_logmarginal<<<(D + 127) / 128, 128, 0, st>>>(d, nc, d_off, d_mem, d_cst, s.d_nlevels.p, use_flags,
+                                                 base_host ? d_base : nullptr, base_scale, out_scale, d_out,
+                                                 flags_host ? c->scratch_u8.p : nullptr,
+                                                 tape_f ? d_tape : nullptr, seed, iter, k);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(out_host, d_out, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  if (flags_host) CK(cudaMemcpyAsync(flags_host, c->scratch_u8.p, D, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int pmdi_feature_null(pmdi_ctx* c, int32_t k, double* out_D) {
+  if (!c || k < 0 || k >= c->K || !c->ds[k].bound) return fail(1, "pmdi_feature_null: dataset not bound");
+  CK(cudaSetDevice(c->device));
+  std::vector<int> off = {0, (int)c->n}, mem(c->n);
+  for (long long i = 0; i < c->n; ++i) mem[i] = (int)i;
+  return run_logmarginal(c, k, off, mem, 0, nullptr, 0.0, -1.0, out_D, nullptr, nullptr, 0, 0);
+}
+
+int pmdi_feature_select(pmdi_ctx* c, int32_t k, const int64_t* labels, const double* feature_null,
+                        uint64_t seed, uint32_t iter, const double* tape_f, double* out_prob_D,
+                        uint8_t* out_flags_D) {
+  if (!c || k < 0 || k >= c->K || !c->ds[k].bound) return fail(1, "pmdi_feature_select: dataset not bound");
+  CK(cudaSetDevice(c->device));
+  const long long n = c->n;
+  // occupied clusters in first-appearance order, members in index order (src/pmdi.jl:358-364)
+  std::vector<int> order_of(c->N + 1, -1), occ;
+  for (long long i = 0; i < n; ++i) {
+    const int64_t l = labels[i];
+    if (l < 1 || l > c->N) return fail(1, "pmdi_feature_select: label outside 1..N");
+    if (order_of[l] < 0) { order_of[l] = (int)occ.size(); occ.push_back((int)l); }
+  }
+  std::vector<int> off(occ.size() + 1, 0), mem(n);
+  for (long long i = 0; i < n; ++i) off[order_of[labels[i]] + 1] += 1;
+  for (size_t i = 0; i < occ.size(); ++i) off[i + 1] += off[i];
+  std::vector<int> w(off.begin(), off.end() - 1);
+  for (long long i = 0; i < n; ++i) mem[w[order_of[labels[i]]]++] = (int)i;
+  return run_logmarginal(c, k, off, mem, 0, feature_null, 1.0, 1.0, out_prob_D, out_flags_D, tape_f, seed, iter);
+}
+
+int pmdi_cluster_eval(pmdi_ctx* c, int32_t k, const int64_t* rows, int64_t m, int64_t obs,
+                      double* out_logprob, double* out_logmarg_D) {
+  if (!c || k < 0 || k >= c->K || !c->ds[k].bound) return fail(1, "pmdi_cluster_eval: dataset not bound");
+  int rc = prepare(c);
+  if (rc) return rc;
+  const long long n = c->n;
+  if (m < 0 || m > n) return fail(1, "pmdi_cluster_eval: bad member count");
+  std::vector<int> mem(m);
+  for (int64_t i = 0; i < m; ++i) {
+    if (rows[i] < 1 || rows[i] > n) return fail(1, "pmdi_cluster_eval: row outside 1..n_obs");
+    mem[i] = (int)(rows[i] - 1);
+  }
+  Dataset& s = c->ds[k];
+  cudaStream_t st = c->stream;
+  if (out_logprob) {
+    if (obs < 1 || obs > n) return fail(1, "pmdi_cluster_eval: obs outside 1..n_obs");
+    CK(c->members.ensure(std::max<size_t>((size_t)c->K * n, 1)));
+    if (m) CK(cudaMemcpyAsync(c->members.p, mem.data(), sizeof(int) * m, cudaMemcpyHostToDevice, st));
+    CK(c->scratch_d.ensure(8));
+    k_build_one<<<(s.Dp + 127) / 128, 128, 0, st>>>(c->sp, k, c->members.p, (int)m);
+    k_aux_one<<<1, 256, 0, st>>>(c->sp, k);
+    k_eval_row<<<1, 32, s.Dp * 8, st>>>(c->sp, k, (int)(obs - 1), c->scratch_d.p);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out_logprob, c->scratch_d.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    // leave the prototype row empty again (rows with n == 0 are always in the empty state)
+    k_build_one<<<(s.Dp + 127) / 128, 128, 0, st>>>(c->sp, k, c->members.p, 0);
+    k_aux_one<<<1, 256, 0, st>>>(c->sp, k);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(st));
+  }
+  if (out_logmarg_D) {
+    std::vector<int> off = {0, (int)m};
+    rc = run_logmarginal(c, k, off, mem, 1, nullptr, 0.0, 1.0, out_logmarg_D, nullptr, nullptr, 0, 0);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,86 @@
+/*
+ * Internal types shared by the host side (pmdi_capi) and the sm_100a kernels of libpmdi_cuda.so.
+ *
+ * HBM layout.  Every particle owns N clusters per dataset ("dense" form of the
+ * reference's copy-on-write pool, src/pmdi.jl:131-146).  A cluster of dataset k
+ * is a ROW r = slot*N + label of Dp feature-contiguous statistics, structure-of-arrays:
+ *   Gaussian     mu[r][q], lamn[r][q] = lambda/(n+1), sum[r][q], beta[r][q]      (f64)
+ *   Categorical  cnt[r][level][q]                                                (u32)
+ *   NegBinom     S[r][q]                                                         (i64)
+ * plus per row: n[r] (cluster size), aux[r][j] (x-independent part of the predictive, per
+ * 256-feature block j), part[r][j] (this step's predictive partial sums).
+ * Slots 0..P-1 are particles (a logical->slot table follows resampling so that survivors are
+ * never copied), slot P holds the rho-prefix prototypes, slot P+1 row 0 is the shared empty
+ * cluster that stands for every label with n == 0.
+ */
+#ifndef PMDI_INTERNAL_H
+#define PMDI_INTERNAL_H
+#include <stdint.h>
+
+#define PMDI_MAX_K 8
+#define PMDI_MAX_N 256
+#define PMDI_FB 256 /* features per work item (one warp, 4 iterations of 64) */
+#define PMDI_WF 64  /* features per warp iteration: 32 lanes x one 128-bit load */
+#define PMDI_NT 512 /* threads per CTA of the sweep kernel */
+
+enum { T_GAUSSIAN = 0, T_CATEGORICAL = 1, T_NEGBINOM = 2 };
+enum { DRAW_ALLOC = 0, DRAW_RESAMP = 1, DRAW_SHUFFLE = 2, DRAW_SELECT = 3, DRAW_FEATURE = 4 };
+
+struct DsDev {
+  int type, D, Dp, J;
+  int Lmax, all_on, x_off /* byte offset of this dataset's row in the smem staging area */, nflag;
+  const void* x;        /* [n_obs][Dp]: f64 (Gaussian) or i32 (others), row-major        */
+  const uint8_t* flag;  /* [Dp], padded features are 0                                    */
+  const double* rc;     /* [n_obs+1] x-independent row constant by cluster size           */
+  double *mu, *lamn, *sum, *beta;
+  uint32_t* cnt;
+  long long* S;
+  double* part;
+  double* aux;
+  int* n;
+};
+
+struct SweepParams {
+  int K, N, P, n_obs, n1, steps;
+  int G, flags;
+  DsDev ds[PMDI_MAX_K];
+  const double* Pi;      /* [K][N]                                          */
+  const double* l1phi;   /* [npairs] log(1+phi)                             */
+  const long long* s_in; /* [K][n_obs] labels 1..N                          */
+  const int* order;      /* [n_obs] 0-based observation per position        */
+  double lw_init;
+  unsigned long long seed;
+  unsigned iter;
+  int Jmax;                /* max over datasets of J                          */
+  const double *tape_alloc, *tape_resamp, *tape_shuffle, *tape_select;
+  /* state */
+  double* lw;             /* [P] by logical particle                         */
+  int* slot_of;           /* [2][P] logical -> slot, double-buffered         */
+  uint8_t* lab;           /* [K][P] by slot: label chosen this step (0-based) */
+  uint8_t* alloc_log;     /* [steps][K][P] by logical particle               */
+  int* anc_log;           /* [events][P] 1-based ancestors                   */
+  int* ev_of_step;        /* [steps] event index or -1                       */
+  /* resampling plan scratch (CTA 0) */
+  double *sc_w, *sc_pp, *sc_u;
+  int *sc_j, *sc_anc0, *sc_a, *sc_b, *sc_c, *sc_d;
+  int2* copies;
+  int* plan_out;          /* [0] number of copies of the current event       */
+  /* static ownership of (dataset, slot) units by CTAs */
+  const int* cta_off;
+  const int* cta_units;   /* k << 24 | slot                                   */
+  int max_units, sm_x_bytes;
+  int lf_T, sm_rowcap;
+  const double* lf_glob;  /* log-factorial table [lf_T]                       */
+  unsigned* bar;          /* grid barrier counter                             */
+  int* err;
+  unsigned long long* rows_eval; /* [K] rows evaluated                        */
+  long long* counters;    /* [0] events, [1] copies                           */
+  unsigned long long* phase_ns;  /* [8] per-phase time of CTA 0 (optional)    */
+  /* debug capture */
+  double* dbg_lp;
+  double* dbg_lw;
+  int* dbg_alloc;
+  int* dbg_anc;
+};
+
+#endif
