@@ -28,6 +28,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "particle*cluster*feature evals/sec (dense count P*N*sum_k D_k per observation step)"
 UNIT = "evals/s"
+PHASES = ["prefetch+offsets", "predictive", "proposal", "cluster_add", "barrier_wait", "weights+ess", "resample"]
 
 # algorithmic bytes per eval / per add at the reference's widths and as stored
 READ_B = {0: 16, 1: 8, 2: 8}
@@ -237,7 +238,7 @@ def run_ours(args):
         resamples += r["n_resamples"]
         ncopies += r["n_copies"]
         evals += r["n_evals"]
-    phase_ms = r["phase_ms"]
+    phase_ms, phase_ms_max = r["phase_ms"], r["phase_ms_max"]
 
     # ---------------------------------------------------------------- end to end (host buffers)
     barrier()
@@ -314,9 +315,8 @@ def run_ours(args):
                         "per observation step at the reference's f64/Int64 widths (SURVEY 8(d)); "
                         "empty labels are not read",
                 "kernel_share_of_step": k_ms / (dev_ms / args.steps),
-                "phase_ms_cta0": {"stage+rowlist": phase_ms[0], "predictive": phase_ms[1],
-                                  "barrier_wait": phase_ms[2], "proposal": phase_ms[3],
-                                  "ess+add": phase_ms[4], "resample": phase_ms[5]},
+                "phase_ms_mean_over_ctas": dict(zip(PHASES, phase_ms[:7])),
+                "phase_ms_max_over_ctas": dict(zip(PHASES, phase_ms_max[:7])),
             },
         }
         if world == 1 and not args.no_cpu:

@@ -34,7 +34,7 @@ extern "C" {
 #define PMDI_SWEEP_DEBUG        1u /* capture per-step lp / log-weights / allocations / ancestors */
 #define PMDI_SWEEP_SSTAR_COMPAT 2u /* emit allocations without following ancestors, as pmdi() does
                                       (src/pmdi.jl:321-324; the tested twin src/__pmdi.jl:285 follows them) */
-#define PMDI_SWEEP_TIME_PHASES  4u /* CTA 0 accumulates per-phase wall time of the sweep kernel (globaltimer) */
+#define PMDI_SWEEP_TIME_PHASES  4u /* every CTA accumulates per-phase wall time of the sweep kernel (globaltimer) */
 
 typedef struct pmdi_ctx pmdi_ctx;
 
@@ -100,8 +100,10 @@ typedef struct pmdi_sweep_out {
   int64_t  rows_evaluated[8]; /* per dataset: cluster rows evaluated over the sweep           */
   double   device_ms;     /* device time of the whole sweep (prefix .. selection), CUDA events */
   double   sweep_kernel_ms;  /* device time of the persistent per-observation kernel alone    */
-  double   phase_ms[6];   /* with PMDI_SWEEP_TIME_PHASES, CTA 0: 0 staging+row list, 1 predictive,
-                             2 barrier wait, 3 proposal, 4 ESS+add, 5 resampling              */
+  double   phase_ms[8];   /* with PMDI_SWEEP_TIME_PHASES, mean over CTAs: 0 prefetch + item offsets,
+                             1 predictive, 2 proposal, 3 cluster_add, 4 grid-barrier wait,
+                             5 weights + ESS, 6 resampling, 7 unused                           */
+  double   phase_ms_max[8]; /* same phases, maximum over CTAs                                  */
   /* debug capture, used when PMDI_SWEEP_DEBUG is set; each may be NULL */
   double*  dbg_lp;        /* [steps][K][P][N]                                                 */
   double*  dbg_lw;        /* [steps][P] after coupling, before resampling                     */

@@ -56,7 +56,8 @@ class SweepOut(C.Structure):
         ("s", C.c_void_p), ("p_star", C.c_void_p), ("logweight", C.c_void_p),
         ("n_resamples", C.c_int64), ("n_copies", C.c_int64), ("n_evals", C.c_int64),
         ("n_evals_dense", C.c_int64), ("rows_evaluated", C.c_int64 * 8),
-        ("device_ms", C.c_double), ("sweep_kernel_ms", C.c_double), ("phase_ms", C.c_double * 6),
+        ("device_ms", C.c_double), ("sweep_kernel_ms", C.c_double), ("phase_ms", C.c_double * 8),
+        ("phase_ms_max", C.c_double * 8),
         ("dbg_lp", C.c_void_p), ("dbg_lw", C.c_void_p), ("dbg_alloc", C.c_void_p),
         ("dbg_anc", C.c_void_p), ("cluster_n", C.c_void_p),
     ]
@@ -230,6 +231,7 @@ class Context:
         res["device_ms"] = float(o.device_ms)
         res["sweep_kernel_ms"] = float(o.sweep_kernel_ms)
         res["phase_ms"] = [float(v) for v in o.phase_ms]
+        res["phase_ms_max"] = [float(v) for v in o.phase_ms_max]
         return res
 
     def sweep(self, s, order_obs, n1, Pi, phi, *, logweight_init=0.0, seed=0, it=0, tapes=None,

@@ -26,9 +26,10 @@ __global__ void k_init_rows(DsDev ds, long long rows) {
 __global__ void k_sweep_init(SweepParams sp) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < sp.P) {
-    sp.lw[t] = sp.lw_init;
     sp.slot_of[t] = t;
     sp.slot_of[sp.P + t] = t;
+    sp.logical_of[t] = t;
+    sp.logical_of[sp.P + t] = t;
   }
   if (t == 0) {
     *sp.bar = 0u;
@@ -152,20 +153,17 @@ __global__ void k_broadcast(SweepParams sp) {
 // Particle selection (StatsBase.sample(1:P, Weights(w)), src/pmdi.jl:345-350), lineage back-trace
 // and s[:] = sstar[p_star,:,:] (src/pmdi.jl:373).  One block.
 __global__ void k_finish(SweepParams sp, int compat, long long* s_out, long long* p_star_out,
-                         double* lw_out, long long* cluster_n, int* cur_at) {
+                         long long* cluster_n, int* cur_at) {
   const int t = threadIdx.x, NT = blockDim.x, P = sp.P, K = sp.K, N = sp.N;
   __shared__ double red[32];
   double mx = -INFINITY;
-  for (int p = t; p < P; p += NT) mx = fmax(mx, sp.lw[p]);
+  for (int p = t; p < P; p += NT) mx = fmax(mx, sp.lw_out[p]);
   mx = warp_max(mx);
   if ((t & 31) == 0) red[t >> 5] = mx;
   __syncthreads();
   mx = red[0];
   for (int i = 1; i < (NT >> 5); ++i) mx = fmax(mx, red[i]);
-  for (int p = t; p < P; p += NT) {
-    sp.sc_w[p] = exp(sp.lw[p] - mx);
-    lw_out[p] = sp.lw[p];
-  }
+  for (int p = t; p < P; p += NT) sp.sc_w[p] = exp(sp.lw_out[p] - mx);
   __syncthreads();
   if (t == 0) {
     double tot = 0.0;
@@ -314,4 +312,49 @@ __global__ void k_aux_one(SweepParams sp, int k) {
     else if (ds.type == T_NEGBINOM) nb_aux_block(ds, row, j, n, lane, sp.lf_glob, sp.lf_T);
     else if (lane == 0) ds.aux[row * ds.J + j] = 0.0;
   }
+}
+
+// Predictive of the EMPTY cluster for every swept observation (it depends on the observation
+// only): lp_empty[step][k] = calc_logprob(x_step, empty cluster of dataset k).  Every label with
+// n == 0 of every particle shares this value.  One block per step; the same block operators as
+// the sweep, applied to the shared empty row.
+__global__ void k_empty_lp(SweepParams sp, double* lp_empty) {
+  extern __shared__ __align__(16) unsigned char xs_raw[];
+  __shared__ double part[PMDI_MAX_K][32];
+  const int step = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+  const int obs = sp.order[sp.n1 - 1 + step];
+  for (int k = 0; k < sp.K; ++k) {
+    const DsDev& ds = sp.ds[k];
+    const int words = ds.Dp * (ds.type == T_GAUSSIAN ? 2 : 1);
+    const int* src = (const int*)ds.xstage + (size_t)obs * words;
+    int* dst = (int*)(xs_raw + ds.x_off);
+    for (int q = tid; q < words; q += blockDim.x) dst[q] = src[q];
+  }
+  __syncthreads();
+  const long long row = (long long)(sp.P + 1) * sp.N;
+  for (int it = warp; it < sp.K * sp.Jmax; it += NW) {
+    const int k = it / sp.Jmax, j = it - k * sp.Jmax;
+    const DsDev& ds = sp.ds[k];
+    if (j >= ds.J) continue;
+    double v;
+    if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, 0, (const double*)(xs_raw + ds.x_off), lane);
+    else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)(xs_raw + ds.x_off), lane);
+    else v = nb_eval_block(ds, row, j, 0, (const int*)(xs_raw + ds.x_off), lane, sp.lf_glob, sp.lf_T);
+    if (lane == 0) part[k][j] = v;
+  }
+  __syncthreads();
+  if (tid < sp.K) {
+    const DsDev& ds = sp.ds[tid];
+    double a = ds.rc[0];
+    for (int j = 0; j < ds.J; ++j) a += part[tid][j];
+    lp_empty[(size_t)step * sp.K + tid] = a;
+  }
+}
+
+// Observation matrix with the feature flags folded in (the sweep stages rows with plain async
+// copies): unflagged / padded features become level 0 (categorical) or -1 (NegBinom).
+__global__ void k_mark_x(const int* x, const uint8_t* flag, int* xq, long long n, int Dp, int skip) {
+  const long long total = n * Dp, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    xq[i] = flag[i % Dp] ? x[i] : skip;
 }

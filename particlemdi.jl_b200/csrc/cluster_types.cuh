@@ -47,9 +47,18 @@ __device__ __forceinline__ double gauss_eval_block(const DsDev& ds, long long ro
   return ldcg_f64(ds.aux + row * ds.J + j) - (0.5 * (double)n + 1.0) * s;
 }
 
-// cluster_add! with the literal operation order of gaussian_cluster.jl:57-63 (no FMA contraction),
-// so the stored statistics carry the same bits as the reference's; n is the size AFTER the add.
-// Returns this lane's share of the new aux (sum of 0.5 log lamn over its flagged features).
+// x / c for a row constant c with rc = RN(1/c): quotient, exact FMA residual, one correction
+// (Markstein): the correctly rounded quotient without the full division sequence.
+__device__ __forceinline__ double div_const(double x, double c, double rc) {
+  const double q = x * rc;
+  const double r = fma(-q, c, x);
+  return fma(r, rc, q);
+}
+
+// cluster_add! in the operation order of gaussian_cluster.jl:57-63 (each quotient correctly
+// rounded, no FMA contraction across the reference's operations), so the stored statistics follow
+// the reference's to the bit; n is the size AFTER the add.  The new aux (sum of 0.5 log lamn over
+// the flagged features) is taken as one log of the lane's product of <= 8 factors.
 __device__ __forceinline__ void gauss_add_block(const DsDev& ds, long long row, int j, int n,
                                                 const double* xs, int lane) {
   const int q0 = j * PMDI_FB;
@@ -61,39 +70,46 @@ __device__ __forceinline__ void gauss_add_block(const DsDev& ds, long long row, 
   const double c4 = __dmul_rn(__dadd_rn(__dmul_rn(0.5, nn), 0.5), c3);  // (n/2 + 1/2)(n + kappa)
   const double c5 = __dadd_rn(nn, 1.001);                       // n + 1 + kappa
   const double c6 = __dadd_rn(nn, 1.0);
+  const double r2 = __drcp_rn(c2), r3 = __drcp_rn(c3), r6 = __drcp_rn(c6);
   const long long base = row * ds.Dp + q0 + 2 * lane;
-  double acc = 0.0;
+  double2 sm[4], bt[4], mu[4], ln[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it)
+    if (it < nit) {
+      const long long o = base + it * PMDI_WF;
+      sm[it] = ldcg_f64x2(ds.sum + o); bt[it] = ldcg_f64x2(ds.beta + o);
+      mu[it] = ldcg_f64x2(ds.mu + o); ln[it] = ldcg_f64x2(ds.lamn + o);
+    }
+  double prod = 1.0;
 #pragma unroll
   for (int it = 0; it < 4; ++it)
     if (it < nit) {
       const long long o = base + it * PMDI_WF;
       const double2 x = *(const double2*)(xs + q0 + it * PMDI_WF + 2 * lane);
-      double2 sm = ldcg_f64x2(ds.sum + o), bt = ldcg_f64x2(ds.beta + o), mu = ldcg_f64x2(ds.mu + o);
-      double2 ln = ldcg_f64x2(ds.lamn + o);
       // padded features carry flag 0: they must not enter aux
       const uchar2 fl = *(const uchar2*)(ds.flag + q0 + it * PMDI_WF + 2 * lane);
       if (fl.x) {
-        sm.x = __dadd_rn(sm.x, x.x);
-        const double dd = __dadd_rn(x.x, -mu.x);
-        bt.x = __dadd_rn(bt.x, __ddiv_rn(__dmul_rn(c1, __dmul_rn(dd, dd)), c2));
-        mu.x = __ddiv_rn(sm.x, c3);
-        ln.x = __ddiv_rn(__ddiv_rn(c4, __dmul_rn(bt.x, c5)), c6);
-        acc += 0.5 * log(ln.x);
+        sm[it].x = __dadd_rn(sm[it].x, x.x);
+        const double dd = __dadd_rn(x.x, -mu[it].x);
+        bt[it].x = __dadd_rn(bt[it].x, div_const(__dmul_rn(c1, __dmul_rn(dd, dd)), c2, r2));
+        mu[it].x = div_const(sm[it].x, c3, r3);
+        ln[it].x = div_const(__ddiv_rn(c4, __dmul_rn(bt[it].x, c5)), c6, r6);
+        prod *= ln[it].x;
       }
       if (fl.y) {
-        sm.y = __dadd_rn(sm.y, x.y);
-        const double dd = __dadd_rn(x.y, -mu.y);
-        bt.y = __dadd_rn(bt.y, __ddiv_rn(__dmul_rn(c1, __dmul_rn(dd, dd)), c2));
-        mu.y = __ddiv_rn(sm.y, c3);
-        ln.y = __ddiv_rn(__ddiv_rn(c4, __dmul_rn(bt.y, c5)), c6);
-        acc += 0.5 * log(ln.y);
+        sm[it].y = __dadd_rn(sm[it].y, x.y);
+        const double dd = __dadd_rn(x.y, -mu[it].y);
+        bt[it].y = __dadd_rn(bt[it].y, div_const(__dmul_rn(c1, __dmul_rn(dd, dd)), c2, r2));
+        mu[it].y = div_const(sm[it].y, c3, r3);
+        ln[it].y = div_const(__ddiv_rn(c4, __dmul_rn(bt[it].y, c5)), c6, r6);
+        prod *= ln[it].y;
       }
-      *(double2*)(ds.sum + o) = sm;
-      *(double2*)(ds.beta + o) = bt;
-      *(double2*)(ds.mu + o) = mu;
-      *(double2*)(ds.lamn + o) = ln;
+      *(double2*)(ds.sum + o) = sm[it];
+      *(double2*)(ds.beta + o) = bt[it];
+      *(double2*)(ds.mu + o) = mu[it];
+      *(double2*)(ds.lamn + o) = ln[it];
     }
-  acc = warp_sum(acc);
+  const double acc = warp_sum(0.5 * log(prod));
   if (lane == 0) ds.aux[row * ds.J + j] = acc;
 }
 

@@ -60,7 +60,8 @@ struct Dataset {
   std::vector<uint8_t> flag;           // [Dp]
   std::vector<double> nlevels;         // categorical [D]
   bool rc_dirty = true;
-  DevBuf<unsigned char> x;
+  DevBuf<unsigned char> x, xq;
+  bool xq_dirty = true;
   DevBuf<uint8_t> d_flag;
   DevBuf<double> rc, d_nlevels;
   DevBuf<double> mu, lamn, sum, beta, part, aux;
@@ -68,7 +69,7 @@ struct Dataset {
   DevBuf<long long> S;
   DevBuf<int> n;
   void release() {
-    x.release(); d_flag.release(); rc.release(); d_nlevels.release();
+    x.release(); xq.release(); d_flag.release(); rc.release(); d_nlevels.release();
     mu.release(); lamn.release(); sum.release(); beta.release(); part.release(); aux.release();
     cnt.release(); S.release(); n.release();
   }
@@ -96,7 +97,8 @@ struct pmdi_ctx {
   DevBuf<long long> s_in, s_out, d_pstar, cluster_n, counters;
   DevBuf<int> order, slot_of, anc_log, ev_of_step, members, mem_off, cur_at, plan_out, err;
   DevBuf<int> sc_j, sc_anc0, sc_a, sc_b, sc_c, sc_d;
-  DevBuf<double> lw, lw_out, sc_w, sc_pp, sc_u;
+  DevBuf<double> lw, lw_out, sc_w, sc_pp, sc_u, inc, lp_empty;
+  DevBuf<int> logical_of;
   DevBuf<uint8_t> lab, alloc_log;
   DevBuf<int2> copies;
   DevBuf<unsigned> bar;
@@ -125,6 +127,7 @@ void fill_dsdev(pmdi_ctx* c, int k, DsDev& d) {
   // padded Gaussian features evaluate to a factor of exactly 1 without the flag test
   if (s.type == T_GAUSSIAN && nflag == s.D) d.all_on = 1;
   d.x = s.x.p; d.flag = s.d_flag.p; d.rc = s.rc.p;
+  d.xstage = (s.type != T_GAUSSIAN && nflag != s.D) ? (const void*)s.xq.p : (const void*)s.x.p;
   d.mu = s.mu.p; d.lamn = s.lamn.p; d.sum = s.sum.p; d.beta = s.beta.p;
   d.cnt = s.cnt.p; d.S = s.S.p; d.part = s.part.p; d.aux = s.aux.p; d.n = s.n.p;
 }
@@ -159,6 +162,12 @@ int build_rc(pmdi_ctx* c, int k) {
   }
   CK(s.rc.ensure(n + 1));
   CK(cudaMemcpyAsync(s.rc.p, rc.data(), sizeof(double) * (n + 1), cudaMemcpyHostToDevice, c->stream));
+  if (s.type != T_GAUSSIAN && nflag != s.D) {  // staging source with the flags folded in
+    CK(s.xq.ensure((size_t)n * s.Dp * 4));
+    k_mark_x<<<c->n_sm * 4, 256, 0, c->stream>>>((const int*)s.x.p, s.d_flag.p, (int*)s.xq.p, n, s.Dp,
+                                                  s.type == T_CATEGORICAL ? 0 : -1);
+    CK(cudaGetLastError());
+  }
   CK(cudaStreamSynchronize(c->stream));
   s.rc_dirty = false;
   return 0;
@@ -189,7 +198,6 @@ int build_layout(pmdi_ctx* c) {
     const Dataset& s = c->ds[k];
     const double w = s.type == T_GAUSSIAN ? 16.0 : (s.type == T_NEGBINOM ? 8.0 : 4.0);
     for (int p = 0; p < P; ++p) units.push_back({w * s.Dp + 64.0, k, p});
-    units.push_back({(w * s.Dp + 64.0) * 0.25, k, P + 1});
   }
   std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
   const int G = c->G;
@@ -213,10 +221,14 @@ int build_layout(pmdi_ctx* c) {
   }
   c->cta_off[G] = (int)c->cta_units.size();
   c->sm_rowcap = c->max_units * N;
+  const int Npad = (N + 31) & ~31;
+  // fixed part of the dynamic shared memory: 2 observation buffers, proposal scratch, unit tables
+  const long long fixed = 2LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 +
+                          (long long)c->sm_rowcap * 4 + (4LL * c->max_units + 1) * 4;
   // log-factorial table in shared memory (NegBinom only)
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  const long long budget = (long long)dev_smem - 8192 - c->sm_x_bytes - (long long)c->sm_rowcap * 4;
+  const long long budget = (long long)dev_smem - 4096 - fixed;
   if (budget < 0) return fail(4, "pmdi: datasets too wide for the shared-memory observation staging");
   c->lf_T = 0;
   if (nb_max_arg >= 0) {
@@ -229,7 +241,7 @@ int build_layout(pmdi_ctx* c) {
     CK(c->lf_dev.ensure(c->lf_T));
     CK(cudaMemcpy(c->lf_dev.p, c->lf_host.data(), sizeof(double) * c->lf_T, cudaMemcpyHostToDevice));
   }
-  c->dyn_smem = (size_t)c->sm_x_bytes + (size_t)c->lf_T * 8 + (size_t)c->sm_rowcap * 4;
+  c->dyn_smem = (size_t)fixed + (size_t)c->lf_T * 8;
   CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
   CK(c->d_cta_off.ensure(c->cta_off.size()));
   CK(c->d_cta_units.ensure(c->cta_units.size()));
@@ -320,11 +332,11 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   for (auto& d : c->ds) d.release();
   DevBuf<double>* dd[] = {&c->lf_dev, &c->Pi, &c->l1phi, &c->tape_alloc, &c->tape_resamp, &c->tape_shuffle,
                           &c->tape_select, &c->lw, &c->lw_out, &c->sc_w, &c->sc_pp, &c->sc_u, &c->dbg_lp,
-                          &c->dbg_lw, &c->scratch_d};
+                          &c->dbg_lw, &c->scratch_d, &c->inc, &c->lp_empty};
   for (auto* b : dd) b->release();
   DevBuf<int>* di[] = {&c->d_cta_off, &c->d_cta_units, &c->order, &c->slot_of, &c->anc_log, &c->ev_of_step,
                        &c->members, &c->mem_off, &c->cur_at, &c->plan_out, &c->err, &c->sc_j, &c->sc_anc0,
-                       &c->sc_a, &c->sc_b, &c->sc_c, &c->sc_d, &c->dbg_alloc, &c->dbg_anc, &c->scratch_i};
+                       &c->sc_a, &c->sc_b, &c->sc_c, &c->sc_d, &c->dbg_alloc, &c->dbg_anc, &c->scratch_i, &c->logical_of};
   for (auto* b : di) b->release();
   DevBuf<long long>* dl[] = {&c->s_in, &c->s_out, &c->d_pstar, &c->cluster_n, &c->counters};
   for (auto* b : dl) b->release();
@@ -350,7 +362,7 @@ int pmdi_set_dataset(pmdi_ctx* c, int32_t k, int32_t type_tag, int32_t elem_kind
   if (!c) return fail(1, "NULL context");
   if (k < 0 || k >= c->K) return fail(1, "pmdi_set_dataset: k out of range");
   if (n_obs != c->n) return fail(1, "pmdi_set_dataset: datasets must have n_obs rows (src/pmdi.jl:52)");
-  if (D < 1 || D > (1 << 20)) return fail(1, "pmdi_set_dataset: bad feature count");
+  if (D < 1 || D > 8192) return fail(1, "pmdi_set_dataset: need 1 <= D <= 8192 features per dataset");
   if (ld < n_obs) return fail(1, "pmdi_set_dataset: ld < n_obs");
   if (type_tag < 0 || type_tag > 2) return fail(1, "pmdi_set_dataset: unknown cluster type tag");
   if ((type_tag == PMDI_GAUSSIAN) != (elem_kind == PMDI_F64))
@@ -373,7 +385,7 @@ int pmdi_set_dataset(pmdi_ctx* c, int32_t k, int32_t type_tag, int32_t elem_kind
     CK(s.x.ensure(h.size() * 8));
     CK(cudaMemcpy(s.x.p, h.data(), h.size() * 8, cudaMemcpyHostToDevice));
   } else {
-    std::vector<int> h((size_t)n * Dp, 0);
+    std::vector<int> h((size_t)n * Dp, type_tag == PMDI_NEGBINOM ? -1 : 0);
     const int64_t* x = (const int64_t*)data;
     s.nlevels.assign(s.D, 0.0);
     long long gmax = 0, max_colsum = 0;
@@ -507,20 +519,22 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
     sp.tape_select = c->tape_select.p;
   }
   // state buffers
-  CK(c->lw.ensure(P)); CK(c->lw_out.ensure(P)); CK(c->slot_of.ensure(2 * (size_t)P));
-  CK(c->lab.ensure((size_t)K * P)); CK(c->alloc_log.ensure((size_t)steps * K * P));
+  CK(c->lw.ensure((size_t)c->G * P)); CK(c->lw_out.ensure(P)); CK(c->slot_of.ensure(2 * (size_t)P));
+  CK(c->logical_of.ensure(2 * (size_t)P)); CK(c->inc.ensure(2 * (size_t)K * P)); CK(c->lp_empty.ensure((size_t)steps * K));
+  CK(c->lab.ensure(2 * (size_t)K * P)); CK(c->alloc_log.ensure((size_t)steps * K * P));
   CK(c->anc_log.ensure((size_t)steps * P)); CK(c->ev_of_step.ensure(steps));
   CK(c->sc_w.ensure(P)); CK(c->sc_pp.ensure(P)); CK(c->sc_u.ensure(P));
   CK(c->sc_j.ensure(P)); CK(c->sc_anc0.ensure(P)); CK(c->sc_a.ensure(P)); CK(c->sc_b.ensure(P));
   CK(c->sc_c.ensure(P)); CK(c->sc_d.ensure(P)); CK(c->copies.ensure(P)); CK(c->plan_out.ensure(4));
   CK(c->bar.ensure(4)); CK(c->err.ensure(4)); CK(c->rows_eval.ensure(PMDI_MAX_K)); CK(c->counters.ensure(4));
-  CK(c->phase_ns.ensure(8)); CK(c->d_pstar.ensure(1)); CK(c->cluster_n.ensure((size_t)K * P * N));
+  CK(c->phase_ns.ensure(8 * (size_t)c->G)); CK(c->d_pstar.ensure(1)); CK(c->cluster_n.ensure((size_t)K * P * N));
   CK(c->members.ensure((size_t)K * std::max<long long>(a->n1 - 1, 1))); CK(c->mem_off.ensure((size_t)K * (N + 1)));
   CK(c->cur_at.ensure(steps));
   sp.n1 = (int)a->n1; sp.steps = steps; sp.flags = (int)a->flags;
   sp.Pi = c->Pi.p; sp.l1phi = c->l1phi.p; sp.s_in = c->s_in.p; sp.order = c->order.p;
   sp.lw_init = a->logweight_init; sp.seed = a->seed; sp.iter = a->iter;
-  sp.lw = c->lw.p; sp.slot_of = c->slot_of.p; sp.lab = c->lab.p; sp.alloc_log = c->alloc_log.p;
+  sp.lw = c->lw.p; sp.lw_out = c->lw_out.p; sp.slot_of = c->slot_of.p; sp.logical_of = c->logical_of.p;
+  sp.inc = c->inc.p; sp.lp_empty = c->lp_empty.p; sp.lab = c->lab.p; sp.alloc_log = c->alloc_log.p;
   sp.anc_log = c->anc_log.p; sp.ev_of_step = c->ev_of_step.p;
   sp.sc_w = c->sc_w.p; sp.sc_pp = c->sc_pp.p; sp.sc_u = c->sc_u.p; sp.sc_j = c->sc_j.p;
   sp.sc_anc0 = c->sc_anc0.p; sp.sc_a = c->sc_a.p; sp.sc_b = c->sc_b.p; sp.sc_c = c->sc_c.p;
@@ -534,7 +548,7 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
     CK(cudaMemsetAsync(c->dbg_anc.p, 0, sizeof(int) * (size_t)steps * P, st));
     sp.dbg_lp = c->dbg_lp.p; sp.dbg_lw = c->dbg_lw.p; sp.dbg_alloc = c->dbg_alloc.p; sp.dbg_anc = c->dbg_anc.p;
   }
-  CK(cudaMemsetAsync(c->phase_ns.p, 0, 64, st));
+  CK(cudaMemsetAsync(c->phase_ns.p, 0, 64 * (size_t)c->G, st));
   c->sweep_flags = a->flags;
   c->uploaded = true;
   c->ran = false;
@@ -561,13 +575,14 @@ int pmdi_sweep_run(pmdi_ctx* c) {
   k_prefix_build<<<dim3((maxDp + 127) / 128, N, K), 128, 0, st>>>(sp, c->members.p, c->mem_off.p);
   k_proto_aux<<<dim3(N, K), 256, 0, st>>>(sp);
   k_broadcast<<<c->n_sm * 8, 256, 0, st>>>(sp);
+  k_empty_lp<<<sp.steps, 256, c->sm_x_bytes, st>>>(sp, c->lp_empty.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev1, st));
   void* args[] = {(void*)&c->sp};
   CK(cudaLaunchCooperativeKernel((const void*)k_sweep, dim3(c->G), dim3(PMDI_NT), args, c->dyn_smem, st));
   CK(cudaEventRecord(c->ev2, st));
   k_finish<<<1, 256, 0, st>>>(sp, (c->sweep_flags & PMDI_SWEEP_SSTAR_COMPAT) ? 1 : 0, c->s_out.p, c->d_pstar.p,
-                              c->lw_out.p, c->cluster_n.p, c->cur_at.p);
+                              c->cluster_n.p, c->cur_at.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev3, st));
   c->ran = true;
@@ -583,12 +598,13 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   const int steps = c->sp.steps;
   int err = 0;
   long long counters[4] = {0, 0, 0, 0};
-  unsigned long long rows[PMDI_MAX_K], phase[8];
+  unsigned long long rows[PMDI_MAX_K];
+  std::vector<unsigned long long> phase(8 * (size_t)c->G, 0ull);
   long long pstar = 0;
   CK(cudaMemcpyAsync(&err, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(counters, c->counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(rows, c->rows_eval.p, sizeof(rows), cudaMemcpyDeviceToHost, st));
-  CK(cudaMemcpyAsync(phase, c->phase_ns.p, sizeof(phase), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(phase.data(), c->phase_ns.p, 8 * sizeof(unsigned long long) * c->G, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&pstar, c->d_pstar.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
   if (o->s) CK(cudaMemcpyAsync(o->s, c->s_out.p, sizeof(int64_t) * n * K, cudaMemcpyDeviceToHost, st));
   if (o->logweight) CK(cudaMemcpyAsync(o->logweight, c->lw_out.p, sizeof(double) * P, cudaMemcpyDeviceToHost, st));
@@ -609,6 +625,7 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   o->n_copies = counters[1];
   long long ev = 0, dense = 0;
   for (int k = 0; k < K; ++k) {
+    rows[k] += (unsigned long long)steps;  // the shared empty cluster: one evaluation per step
     ev += (long long)rows[k] * c->ds[k].D;
     dense += (long long)steps * P * N * c->ds[k].D;
     o->rows_evaluated[k] = (int64_t)rows[k];
@@ -621,7 +638,16 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   o->device_ms = ms;
   CK(cudaEventElapsedTime(&ms, c->ev1, c->ev2));
   o->sweep_kernel_ms = ms;
-  for (int i = 0; i < 6; ++i) o->phase_ms[i] = (double)phase[i] * 1e-6;
+  for (int i = 0; i < 8; ++i) {
+    double mean = 0.0, mx = 0.0;
+    for (int g = 0; g < c->G; ++g) {
+      const double v = (double)phase[(size_t)g * 8 + i] * 1e-6;
+      mean += v / c->G;
+      mx = std::max(mx, v);
+    }
+    o->phase_ms[i] = mean;
+    o->phase_ms_max[i] = mx;
+  }
   return 0;
 }
 

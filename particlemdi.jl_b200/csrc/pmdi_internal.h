@@ -30,6 +30,7 @@ struct DsDev {
   int type, D, Dp, J;
   int Lmax, all_on, x_off /* byte offset of this dataset's row in the smem staging area */, nflag;
   const void* x;        /* [n_obs][Dp]: f64 (Gaussian) or i32 (others), row-major        */
+  const void* xstage;   /* what the sweep stages: x, or x with the feature flags folded in */
   const uint8_t* flag;  /* [Dp], padded features are 0                                    */
   const double* rc;     /* [n_obs+1] x-independent row constant by cluster size           */
   double *mu, *lamn, *sum, *beta;
@@ -54,9 +55,13 @@ struct SweepParams {
   int Jmax;                /* max over datasets of J                          */
   const double *tape_alloc, *tape_resamp, *tape_shuffle, *tape_select;
   /* state */
-  double* lw;             /* [P] by logical particle                         */
-  int* slot_of;           /* [2][P] logical -> slot, double-buffered         */
-  uint8_t* lab;           /* [K][P] by slot: label chosen this step (0-based) */
+  double* lw;             /* [G][P] per-CTA private copy of the log-weights, by logical particle */
+  double* lw_out;         /* [P] final log-weights (written by CTA 0)        */
+  int* slot_of;           /* [2][P] logical -> slot, double-buffered by resampling event */
+  int* logical_of;        /* [2][P] slot -> logical                          */
+  uint8_t* lab;           /* [2][K][P] by slot: label chosen this step (0-based), double-buffered by step */
+  double* inc;            /* [2][K][P] by slot: incremental log-weight of this step              */
+  const double* lp_empty; /* [steps][K] predictive of the empty cluster for every swept observation */
   uint8_t* alloc_log;     /* [steps][K][P] by logical particle               */
   int* anc_log;           /* [events][P] 1-based ancestors                   */
   int* ev_of_step;        /* [steps] event index or -1                       */
@@ -75,7 +80,7 @@ struct SweepParams {
   int* err;
   unsigned long long* rows_eval; /* [K] rows evaluated                        */
   long long* counters;    /* [0] events, [1] copies                           */
-  unsigned long long* phase_ns;  /* [8] per-phase time of CTA 0 (optional)    */
+  unsigned long long* phase_ns;  /* [G][8] per-CTA per-phase time (optional)  */
   /* debug capture */
   double* dbg_lp;
   double* dbg_lw;

@@ -1,30 +1,30 @@
 // The conditional-SMC sweep as ONE persistent cooperative kernel: the per-observation loop of
-// the reference (src/pmdi.jl:209-342) runs on the device with two grid barriers per step and no
-// host involvement.  One CTA per SM; every (dataset, particle-slot) unit of statistics is owned
-// by one CTA for the whole sweep, so the add of step t and the predictive of step t+1 need no
-// grid-wide ordering.
+// the reference (src/pmdi.jl:209-342) runs on the device with ONE grid barrier per observation
+// and no host involvement.  One CTA per SM.  Every (dataset, particle-slot) unit of statistics
+// is owned by one CTA for the whole sweep, so predictive, proposal and add of a unit are
+// CTA-local; only the particle weights need the whole grid.
 //
 //   phase A  predictive      calc_logprob for every occupied cluster row of the CTA's units
 //                            (src/pmdi.jl:218-220) -> part[row][block]
-//   -- grid barrier --
-//   phase B  proposal        per particle and dataset: sum partials, softmax-cdf, draw, weight
-//                            increment (src/pmdi.jl:223-265); Phi coupling (src/misc.jl:50-59)
-//   -- grid barrier --
-//   phase E  ESS             every CTA evaluates calc_ESS (src/misc.jl:15-25) redundantly
+//   phase B  proposal        per owned unit: sum partials, softmax-cdf, draw, weight increment
+//                            (src/pmdi.jl:223-265) -> lab/inc[step parity][k][slot]
 //   phase C  cluster_add!    chosen row of every owned unit (src/pmdi.jl:275-310, dense form)
+//   -- grid barrier --
+//   phase E  weights + ESS   every CTA folds all increments and the Phi coupling
+//                            (src/misc.jl:50-59) into its private copy of the log-weights and
+//                            evaluates calc_ESS (src/misc.jl:15-25): identical bits everywhere
 //   [resampling steps only]  CTA 0: draw_partstar (src/misc.jl:27-47) + copy plan; barrier;
 //                            all CTAs move the duplicated particles' rows; barrier
+//
+// The observation rows are prefetched one step ahead with cp.async into a double buffer.
 #pragma once
 #include "cluster_types.cuh"
 
 struct SweepSmem {
   double red[3 * 32];
-  double lp_empty[PMDI_MAX_K];
-  double inc[PMDI_NT / 32];
-  int lab[PMDI_NT / 32];
-  int n_entries;
   int item_ctr;
-  int flag;
+  int total_items;
+  int plan_drop;
   unsigned rows_eval[PMDI_MAX_K];
 };
 
@@ -74,16 +74,18 @@ __device__ int block_excl_scan(const int* in, int* out, int P, int* s_tmp /* PMD
 }
 
 // draw_partstar (src/misc.jl:27-47) + the slot plan, by CTA 0.  Output: anc_log[ev][P] (1-based),
-// slot_of[next][P], copies[], plan_out[0] = number of copies.
+// slot_of/logical_of[next][P], copies[], plan_out[0] = number of copies.
 // The Fisher-Yates shuffle followed by partstar[1]=1 and sort! only decides WHICH element of the
 // sorted systematic sample is replaced by the reference particle: the one the shuffle moves to
 // position 1.  That index is traced through the swaps without moving anything.
-__device__ void resample_plan(const SweepParams& sp, int step, int ev, double mx, int* s_tmp) {
+__device__ void resample_plan(const SweepParams& sp, int step, int ev, double mx, const double* lw,
+                              int* s_tmp) {
   const int P = sp.P, t = threadIdx.x;
   const int* slot_cur = sp.slot_of + (ev & 1) * P;
   int* slot_nxt = sp.slot_of + ((ev + 1) & 1) * P;
+  int* logi_nxt = sp.logical_of + ((ev + 1) & 1) * P;
   for (int p = t; p < P; p += PMDI_NT) {
-    sp.sc_w[p] = exp(ldcg_f64(sp.lw + p) - mx);
+    sp.sc_w[p] = exp(lw[p] - mx);
     // Fisher-Yates pick for position pos = p+1 (entry index p), pos >= 2
     const double us = sp.tape_shuffle ? sp.tape_shuffle[(size_t)step * P + p]
                                       : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_SHUFFLE, step, 0, p);
@@ -111,7 +113,7 @@ __device__ void resample_plan(const SweepParams& sp, int step, int ev, double mx
   const double tot = sp.sc_pp[P - 1];
   for (int i = t; i < P; i += PMDI_NT) {  // first p with pprob[p]/last >= u_i (misc.jl:33-38)
     const double ui = sp.sc_u[i];
-    int lo = 0, hi = P;  // answer in [lo, hi]; hi == P means none
+    int lo = 0, hi = P;  // hi == P means none
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (sp.sc_pp[mid] / tot >= ui) hi = mid; else lo = mid + 1;
@@ -143,19 +145,27 @@ __device__ void resample_plan(const SweepParams& sp, int step, int ev, double mx
   __syncthreads();
   for (int i = t; i < P; i += PMDI_NT) {
     const int src = ldcg_i32(slot_cur + anc[i] - 1);
+    int dst = src;
     if (sp.sc_a[i]) {
-      const int dst = sp.sc_j[sp.sc_c[i]];
-      slot_nxt[i] = dst;
+      dst = sp.sc_j[sp.sc_c[i]];
       sp.copies[sp.sc_c[i]] = make_int2(src, dst);
-    } else {
-      slot_nxt[i] = src;
     }
+    slot_nxt[i] = dst;
+    logi_nxt[dst] = i;
   }
   if (t == 0) {
     sp.plan_out[0] = n_extra;
     sp.ev_of_step[step] = ev;
   }
   __syncthreads();
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepParams sp) {
@@ -167,22 +177,30 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
   const int NW = PMDI_NT / 32;
   const int cta = blockIdx.x, G = sp.G;
   const int K = sp.K, N = sp.N, P = sp.P;
+  const int Npad = (N + 31) & ~31;
 
-  unsigned char* xs_raw = smem_raw;
-  double* lf = (double*)(smem_raw + sp.sm_x_bytes);
-  unsigned* rowlist = (unsigned*)(smem_raw + sp.sm_x_bytes + (size_t)sp.lf_T * 8);
+  // dynamic shared memory: [x buffer 0][x buffer 1][lf table][lp scratch NW x Npad][unit tables]
+  unsigned char* xbuf[2] = {smem_raw, smem_raw + sp.sm_x_bytes};
+  double* lf = (double*)(smem_raw + 2 * (size_t)sp.sm_x_bytes);
+  double* lp_s = lf + sp.lf_T;
+  unsigned* urow = (unsigned*)(lp_s + (size_t)NW * Npad);   // [nu][N]: label | n << 8
+  const int u0 = sp.cta_off[cta], nu = sp.cta_off[cta + 1] - u0;
+  int* ucount = (int*)(urow + (size_t)sp.max_units * N);     // [max_units]
+  int* uoff = ucount + sp.max_units;                         // [max_units + 1]
+  int* uinfo = uoff + sp.max_units + 1;                      // [max_units] k << 24 | slot
+  int* ulab = uinfo + sp.max_units;                          // [max_units] label chosen this step
   const int lfT = sp.lf_T;
   for (int i = tid; i < lfT; i += PMDI_NT) lf[i] = sp.lf_glob[i];
   if (tid < PMDI_MAX_K) sm.rows_eval[tid] = 0;
+  for (int u = tid; u < nu; u += PMDI_NT) uinfo[u] = sp.cta_units[u0 + u];
 
-  const int u0 = sp.cta_off[cta], u1 = sp.cta_off[cta + 1];
-  const int empty_slot = P + 1;
-  const long long empty_row = (long long)empty_slot * N;
+  double* lw = sp.lw + (size_t)cta * P;  // private copy, thread t owns p = t, t + NT, ...
+  for (int p = tid; p < P; p += PMDI_NT) lw[p] = sp.lw_init;
 
   unsigned epoch = 0;
   int ev = 0;
-  const bool timing = sp.phase_ns != nullptr && cta == 0 && tid == 0;
-  unsigned long long tacc[6] = {0, 0, 0, 0, 0, 0}, t_prev = 0;
+  const bool timing = sp.phase_ns != nullptr && tid == 0;
+  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_prev = 0;
   if (timing) t_prev = globaltimer_ns();
 #define PHASE_MARK(i_)                                   \
   if (timing) {                                          \
@@ -191,221 +209,254 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
     t_prev = now_;                                       \
   }
 
-  // B-phase geometry: warp (pl, k) of a CTA round handles dataset k of one particle
-  const int ppb = NW / K;
-  const int b_rounds = (P + ppb * G - 1) / (ppb * G);
-
-  for (int step = 0; step < sp.steps; ++step) {
+  // occupied rows of every owned unit, from the statistics in HBM
+  auto rebuild_rows = [&]() {
+    for (int u = warp; u < nu; u += NW) {
+      const int k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
+      int cnt = 0;
+      for (int m0 = 0; m0 < N; m0 += 32) {
+        const int m = m0 + lane;
+        const int nm = (m < N) ? ldcg_i32(sp.ds[k].n + (long long)slot * N + m) : 0;
+        const unsigned b = __ballot_sync(FULL, nm > 0);
+        if (nm > 0) urow[(size_t)u * N + cnt + __popc(b & ((1u << lane) - 1))] = (unsigned)m | ((unsigned)nm << 8);
+        cnt += __popc(b);
+      }
+      if (lane == 0) ucount[u] = cnt;
+    }
+  };
+  // stage (asynchronously) the observation of one step into buffer b
+  auto prefetch_obs = [&](int step, int b) {
+    if (step >= sp.steps) return;
     const int obs = sp.order[sp.n1 - 1 + step];
-    const int* slot_cur = sp.slot_of + (ev & 1) * P;
-
-    // ------------------------------------------------------------------ stage the observation
     for (int k = 0; k < K; ++k) {
       const DsDev& ds = sp.ds[k];
-      if (ds.type == T_GAUSSIAN) {
-        const double* src = (const double*)ds.x + (size_t)obs * ds.Dp;
-        double* dst = (double*)(xs_raw + ds.x_off);
-        for (int q = tid; q < ds.Dp; q += PMDI_NT) dst[q] = src[q];
-      } else {
-        const int* src = (const int*)ds.x + (size_t)obs * ds.Dp;
-        int* dst = (int*)(xs_raw + ds.x_off);
-        const int skip = ds.type == T_CATEGORICAL ? 0 : -1;
-        for (int q = tid; q < ds.Dp; q += PMDI_NT) dst[q] = ds.flag[q] ? src[q] : skip;
-      }
+      const int bytes = ds.Dp * (ds.type == T_GAUSSIAN ? 8 : 4);
+      const unsigned char* src = (const unsigned char*)ds.xstage + (size_t)obs * bytes;
+      unsigned char* dst = xbuf[b] + ds.x_off;
+      for (int o = tid * 16; o < bytes; o += PMDI_NT * 16) cp_async16(dst + o, src + o);
     }
-    if (tid == 0) { sm.n_entries = 0; sm.item_ctr = 0; }
-    __syncthreads();
-    // ------------------------------------------------------------------ occupied rows of my units
-    for (int idx = tid; idx < (u1 - u0) * N; idx += PMDI_NT) {
-      const int ul = idx / N, m = idx - ul * N;
-      const int unit = sp.cta_units[u0 + ul];
-      const int k = unit >> 24, slot = unit & 0xFFFFFF;
-      bool occ;
-      if (slot == empty_slot) occ = (m == 0);
-      else occ = ldcg_i32(sp.ds[k].n + (long long)slot * N + m) > 0;
-      if (occ) {
-        const int e = atomicAdd(&sm.n_entries, 1);
-        rowlist[e] = ((unsigned)ul << 8) | (unsigned)m;
-        atomicAdd(&sm.rows_eval[k], 1u);
+  };
+
+  __syncthreads();  // uinfo is visible to every warp
+  rebuild_rows();
+  prefetch_obs(0, 0);
+
+  for (int step = 0; step < sp.steps; ++step) {
+    const int par = step & 1;
+    const unsigned char* xs_raw = xbuf[par];
+    const int* logi_cur = sp.logical_of + (ev & 1) * P;
+    const int* slot_cur = sp.slot_of + (ev & 1) * P;
+    uint8_t* lab_g = sp.lab + (size_t)par * K * P;
+    double* inc_g = sp.inc + (size_t)par * K * P;
+
+    cp_async_commit_wait_all();   // this step's observation has landed (own copies)
+    __syncthreads();              // ... everybody's; previous step's add is complete too
+    prefetch_obs(step + 1, par ^ 1);
+    if (warp == 0) {  // item offsets of the units: uoff[u] = sum_{v<u} ucount[v] * J_v
+      int run = 0;
+      for (int ub = 0; ub < nu; ub += 32) {
+        const int u = ub + lane;
+        int c = 0;
+        if (u < nu) c = ucount[u] * sp.ds[uinfo[u] >> 24].J;
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int v = __shfl_up_sync(FULL, inc, o);
+          if (lane >= o) inc += v;
+        }
+        if (u < nu) uoff[u] = run + inc - c;
+        run += __shfl_sync(FULL, inc, 31);
       }
+      if (lane == 0) { uoff[nu] = run; sm.total_items = run; sm.item_ctr = 0; }
     }
     __syncthreads();
     PHASE_MARK(0)
     // ------------------------------------------------------------------ phase A: predictive
     {
-      const int n_entries = sm.n_entries;
-      const int JM = sp.Jmax;  // item index space per entry
-      // items are (entry, block) pairs handed out dynamically to warps
+      const int total = sm.total_items;
       for (;;) {
         int it = 0;
         if (lane == 0) it = atomicAdd(&sm.item_ctr, 1);
         it = __shfl_sync(FULL, it, 0);
-        // decode: walk entries in order; entry e contributes J_k(e) items
-        // (n_entries * J is small; a flat decode by division on the max J wastes few grabs)
-        const int e = it / JM, j = it - e * JM;
-        if (e >= n_entries) break;
-        const unsigned ent = rowlist[e];
-        const int ul = ent >> 8, m = ent & 0xFF;
-        const int unit = sp.cta_units[u0 + ul];
-        const int k = unit >> 24, slot = unit & 0xFFFFFF;
+        if (it >= total) break;
+        int lo = 0, hi = nu - 1;  // last u with uoff[u] <= it
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (uoff[mid] <= it) lo = mid; else hi = mid - 1;
+        }
+        const int u = lo, k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
         const DsDev& ds = sp.ds[k];
-        if (j >= ds.J) continue;
+        const int r = it - uoff[u];
+        const int e = r / ds.J, j = r - e * ds.J;
+        const unsigned ent = urow[(size_t)u * N + e];
+        const int m = ent & 0xFF, n = ent >> 8;
         const long long row = (long long)slot * N + m;
         double v;
-        if (ds.type == T_GAUSSIAN) {
-          const int n = (slot == empty_slot) ? 0 : ldcg_i32(ds.n + row);
-          v = gauss_eval_block(ds, row, j, n, (const double*)(xs_raw + ds.x_off), lane);
-        } else if (ds.type == T_CATEGORICAL) {
-          v = cat_eval_block(ds, row, j, (const int*)(xs_raw + ds.x_off), lane);
-        } else {
-          const int n = (slot == empty_slot) ? 0 : ldcg_i32(ds.n + row);
-          v = nb_eval_block(ds, row, j, n, (const int*)(xs_raw + ds.x_off), lane, lf, lfT);
-        }
+        if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, n, (const double*)(xs_raw + ds.x_off), lane);
+        else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)(xs_raw + ds.x_off), lane);
+        else v = nb_eval_block(ds, row, j, n, (const int*)(xs_raw + ds.x_off), lane, lf, lfT);
         if (lane == 0) ds.part[row * ds.J + j] = v;
       }
     }
-    PHASE_MARK(1)
-    if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
-    PHASE_MARK(2)
-
-    // ------------------------------------------------------------------ phase B: proposal
-    if (warp < K) {
-      const DsDev& ds = sp.ds[warp];
-      double acc = ds.rc[0];
-      for (int j = 0; j < ds.J; ++j) acc += ldcg_f64(ds.part + empty_row * ds.J + j);
-      if (lane == 0) sm.lp_empty[warp] = acc;
-    }
     __syncthreads();
-    for (int r = 0; r < b_rounds; ++r) {
-      const int pl = warp / K, k = warp - pl * K;
-      const int p = (r * G + cta) * ppb + pl;  // logical particle
-      const bool active = (pl < ppb) && (p < P);
-      int label = 0;
-      double inc = 0.0;
-      if (active) {
-        const DsDev& ds = sp.ds[k];
-        const int slot = ldcg_i32(slot_cur + p);
-        const long long row0 = (long long)slot * N;
-        double lpv[PMDI_MAX_N / 32];
-        double mx = -INFINITY;
+    PHASE_MARK(1)
+    // ------------------------------------------------------------------ phase B: proposal
+    for (int u = warp; u < nu; u += NW) {
+      const int k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
+      const DsDev& ds = sp.ds[k];
+      const int p = ldcg_i32(logi_cur + slot);  // logical particle (RNG address, trajectory log)
+      const long long row0 = (long long)slot * N;
+      double* lps = lp_s + (size_t)warp * Npad;
+      const double lpe = sp.lp_empty[(size_t)step * K + k];
+      for (int m = lane; m < Npad; m += 32) lps[m] = lpe;
+      __syncwarp();
+      const int cnt = ucount[u];
+      for (int e = lane; e < cnt; e += 32) {
+        const unsigned ent = urow[(size_t)u * N + e];
+        const int m = ent & 0xFF, nm = ent >> 8;
+        const double* pp = ds.part + (row0 + m) * ds.J;
+        double a = ds.rc[nm];
+        for (int j0 = 0; j0 < ds.J; j0 += 8) {
+          double v[8];
 #pragma unroll
-        for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+          for (int j = 0; j < 8; ++j) v[j] = (j0 + j < ds.J) ? __ldcg(pp + j0 + j) : 0.0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) if (j0 + j < ds.J) a += v[j];
+        }
+        lps[m] = a;
+      }
+      __syncwarp();
+      double lpv[PMDI_MAX_N / 32];
+      double mx = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+        lpv[c] = -INFINITY;
+        if (c * 32 < N) {
           const int m = c * 32 + lane;
-          lpv[c] = -INFINITY;
           if (m < N) {
-            const int nm = ldcg_i32(ds.n + row0 + m);
-            double a;
-            if (nm > 0) {
-              a = ds.rc[nm];
-              const double* pp = ds.part + (row0 + m) * ds.J;
-              for (int j = 0; j < ds.J; ++j) a += ldcg_f64(pp + j);
-            } else {
-              a = sm.lp_empty[k];
-            }
-            lpv[c] = a;
-            mx = fmax(mx, a);
-            if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = a;
+            lpv[c] = lps[m];
+            mx = fmax(mx, lpv[c]);
+            if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = lpv[c];
           }
         }
-        mx = warp_max(mx);
-        // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
-        double cv[PMDI_MAX_N / 32];
-        double run = 0.0;
+      }
+      mx = warp_max(mx);
+      // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
+      double cv[PMDI_MAX_N / 32];
+      double run = 0.0;
 #pragma unroll
-        for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+      for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+        cv[c] = 0.0;
+        if (c * 32 < N) {
           const int m = c * 32 + lane;
           double f = 0.0;
           if (m < N) f = exp(lpv[c] - mx) * sp.Pi[k * N + m];
-          cv[c] = 0.0;
-          if (c * 32 < N) {
-            const int lim = min(32, N - c * 32);
+          const int lim = min(32, N - c * 32);
 #pragma unroll 1
-            for (int l = 0; l < lim; ++l) {
-              run += __shfl_sync(FULL, f, l);
-              if (lane == l) cv[c] = run;
-            }
+          for (int l = 0; l < lim; ++l) {
+            run += __shfl_sync(FULL, f, l);
+            if (lane == l) cv[c] = run;
           }
         }
-        const double tot = run;
-        inc = log(tot) + mx;
-        if (p == 0) {
-          label = (int)sp.s_in[(size_t)k * sp.n_obs + obs] - 1;  // reference trajectory (:262)
-        } else {
-          const double u = sp.tape_alloc ? sp.tape_alloc[((size_t)step * K + k) * P + p]
-                                         : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
-          label = N - 1;
-          bool found = false;
+      }
+      const double tot = run;
+      const double inc = log(tot) + mx;
+      int label;
+      if (p == 0) {
+        label = (int)sp.s_in[(size_t)k * sp.n_obs + sp.order[sp.n1 - 1 + step]] - 1;  // reference trajectory (:262)
+      } else {
+        const double uu = sp.tape_alloc ? sp.tape_alloc[((size_t)step * K + k) * P + p]
+                                        : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
+        label = N - 1;
+        bool found = false;
 #pragma unroll
-          for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
-            if (c * 32 < N && !found) {
-              const int m = c * 32 + lane;
-              const bool hit = (m < N - 1) && (cv[c] / tot > u);  // strict '>' (:255)
-              const unsigned b = __ballot_sync(FULL, hit);
-              if (b) { label = c * 32 + __ffs(b) - 1; found = true; }
-            }
+        for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+          if (c * 32 < N && !found) {
+            const int m = c * 32 + lane;
+            const bool hit = (m < N - 1) && (cv[c] / tot > uu);  // strict '>' (:255)
+            const unsigned b = __ballot_sync(FULL, hit);
+            if (b) { label = c * 32 + __ffs(b) - 1; found = true; }
           }
         }
-        if (lane == 0) {
-          sp.lab[(size_t)k * P + slot] = (uint8_t)label;
-          sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
-          ds.n[row0 + label] = ldcg_i32(ds.n + row0 + label) + 1;
-          if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
-          sm.inc[warp] = inc;
-          sm.lab[warp] = label;
-        }
       }
-      __syncthreads();
-      if (active && k == 0 && lane == 0) {  // weight update in dataset order, then Phi coupling
-        double w = ldcg_f64(sp.lw + p);
-        for (int kk = 0; kk < K; ++kk) w += sm.inc[pl * K + kk];
-        int idx = 0;
-        for (int k1 = 0; k1 < K - 1; ++k1)
-          for (int k2 = k1 + 1; k2 < K; ++k2) {
-            w += (sm.lab[pl * K + k1] == sm.lab[pl * K + k2]) ? sp.l1phi[idx] : 0.0;
-            ++idx;
-          }
-        sp.lw[p] = w;
-        if (sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
+      // bookkeeping of the chosen row: size, occupied-row list
+      int pos = -1;
+      for (int e0 = 0; e0 < cnt; e0 += 32) {
+        const int e = e0 + lane;
+        const bool hit = (e < cnt) && ((int)(urow[(size_t)u * N + e] & 0xFF) == label);
+        const unsigned b = __ballot_sync(FULL, hit);
+        if (b) { pos = e0 + __ffs(b) - 1; break; }
       }
-      __syncthreads();
+      if (lane == 0) {
+        if (pos >= 0) urow[(size_t)u * N + pos] += (1u << 8);
+        else { urow[(size_t)u * N + cnt] = (unsigned)label | (1u << 8); ucount[u] = cnt + 1; }
+        const int n_new = (pos >= 0 ? (int)(urow[(size_t)u * N + pos] >> 8) : 1);
+        ds.n[row0 + label] = n_new;
+        ulab[u] = label | (n_new << 8);
+        lab_g[(size_t)k * P + slot] = (uint8_t)label;
+        inc_g[(size_t)k * P + slot] = inc;
+        sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
+        if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
+        atomicAdd(&sm.rows_eval[k], (unsigned)cnt);
+      }
     }
-    PHASE_MARK(3)
-    if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
+    __syncthreads();
     PHASE_MARK(2)
-
-    // ------------------------------------------------------------------ phase E: ESS (redundant)
-    double mx = -INFINITY;
-    for (int p = tid; p < P; p += PMDI_NT) mx = fmax(mx, ldcg_f64(sp.lw + p));
-    mx = block_max(mx, sm.red);
-    double num = 0.0, den = 0.0;
-    for (int p = tid; p < P; p += PMDI_NT) {
-      const double w = exp(ldcg_f64(sp.lw + p) - mx);
-      num += w;
-      den += w * w;
-    }
-    block_sum2(num, den, sm.red);
-    const bool do_res = (num * num) / den <= 0.5 * (double)P;
-    if (!do_res && cta == 0 && tid == 0) sp.ev_of_step[step] = -1;
-
-    if (do_res && cta == 0) resample_plan(sp, step, ev, mx, s_tmp);
-
     // ------------------------------------------------------------------ phase C: cluster_add!
-    for (int it = warp; it < (u1 - u0) * sp.Jmax; it += NW) {
-      const int ul = it / sp.Jmax, j = it - ul * sp.Jmax;
-      const int unit = sp.cta_units[u0 + ul];
-      const int k = unit >> 24, slot = unit & 0xFFFFFF;
+    for (int it = warp; it < nu * sp.Jmax; it += NW) {
+      const int u = it / sp.Jmax, j = it - u * sp.Jmax;
+      const int k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
       const DsDev& ds = sp.ds[k];
-      if (slot == empty_slot || j >= ds.J) continue;
-      const int label = ldcg_u8(sp.lab + (size_t)k * P + slot);
+      if (j >= ds.J) continue;
+      const int label = ulab[u] & 0xFF, n = ulab[u] >> 8;  // n = size after the add
       const long long row = (long long)slot * N + label;
-      const int n = ldcg_i32(ds.n + row);
       if (ds.type == T_GAUSSIAN) gauss_add_block(ds, row, j, n, (const double*)(xs_raw + ds.x_off), lane);
       else if (ds.type == T_CATEGORICAL) cat_add_block(ds, row, j, (const int*)(xs_raw + ds.x_off), lane);
       else nb_add_block(ds, row, j, n, (const int*)(xs_raw + ds.x_off), lane, lf, lfT);
     }
+    PHASE_MARK(3)
+    if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
     PHASE_MARK(4)
 
+    // ------------------------------------------------------------------ phase E: weights + ESS
+    double mx = -INFINITY;
+    for (int p = tid; p < P; p += PMDI_NT) {
+      const int slot = ldcg_i32(slot_cur + p);
+      double w = lw[p];
+      int labs[PMDI_MAX_K];
+#pragma unroll
+      for (int k = 0; k < PMDI_MAX_K; ++k)
+        if (k < K) {
+          w += ldcg_f64(inc_g + (size_t)k * P + slot);  // dataset order, as src/pmdi.jl:210,233
+          labs[k] = ldcg_u8(lab_g + (size_t)k * P + slot);
+        }
+      int idx = 0;
+#pragma unroll
+      for (int k1 = 0; k1 < PMDI_MAX_K - 1; ++k1)
+#pragma unroll
+        for (int k2 = k1 + 1; k2 < PMDI_MAX_K; ++k2)
+          if (k2 < K) {
+            w += (labs[k1] == labs[k2]) ? sp.l1phi[idx] : 0.0;  // Phi_upweight! (misc.jl:50-59)
+            ++idx;
+          }
+      lw[p] = w;
+      mx = fmax(mx, w);
+      if (cta == 0 && sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
+    }
+    mx = block_max(mx, sm.red);
+    double num = 0.0, den = 0.0;
+    for (int p = tid; p < P; p += PMDI_NT) {
+      const double w = exp(lw[p] - mx);
+      num += w;
+      den += w * w;
+    }
+    block_sum2(num, den, sm.red);
+    const bool do_res = (num * num) / den <= 0.5 * (double)P;  // src/pmdi.jl:317
+    if (!do_res && cta == 0 && tid == 0) sp.ev_of_step[step] = -1;
+    PHASE_MARK(5)
+
     if (do_res) {
+      if (cta == 0) resample_plan(sp, step, ev, mx, lw, s_tmp);
       if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
       const int ncopy = ldcg_i32(sp.plan_out);
       const int gw = cta * NW + warp, GW = G * NW;
@@ -415,20 +466,20 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
         const int2 cp = __ldcg(sp.copies + c);
         row_copy(sp.ds[k], (long long)cp.x * N + m, (long long)cp.y * N + m, lane);
       }
-      if (cta == 0) {
-        for (int p = tid; p < P; p += PMDI_NT) sp.lw[p] = 1.0;  // logweight .= 1.0 (:319)
-        if (tid == 0) { sp.counters[0] += 1; sp.counters[1] += ncopy; }
-      }
+      for (int p = tid; p < P; p += PMDI_NT) lw[p] = 1.0;  // logweight .= 1.0 (src/pmdi.jl:319)
+      if (cta == 0 && tid == 0) { sp.counters[0] += 1; sp.counters[1] += ncopy; }
       ++ev;
       if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
-      PHASE_MARK(5)
-    } else {
-      __syncthreads();  // adds of this step are visible to the whole CTA before the next predictive
+      rebuild_rows();
+      PHASE_MARK(6)
     }
   }
+  __syncthreads();
   if (tid < K) atomicAdd(sp.rows_eval + tid, (unsigned long long)sm.rows_eval[tid]);
+  if (cta == 0)
+    for (int p = tid; p < P; p += PMDI_NT) sp.lw_out[p] = lw[p];
   if (timing)
-    for (int i = 0; i < 6; ++i) sp.phase_ns[i] = tacc[i];
+    for (int i = 0; i < 8; ++i) sp.phase_ns[(size_t)cta * 8 + i] = tacc[i];
   if (cta == 0 && tid == 0) sp.counters[2] = ev;
 #undef PHASE_MARK
 }

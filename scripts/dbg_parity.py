@@ -12,7 +12,7 @@ o = orc.Oracle(pr["data"], pr["types"], pr["N"], pr["P"])
 ctx = capi.Context(pr["data"], pr["types"], pr["N"], pr["P"])
 ref = o.sweep(pr["s"], pr["order"], pr["n1"], pr["Pi"], pr["phi"], seed=11, it=3, debug=True)
 got = ctx.sweep(pr["s"], pr["order"], pr["n1"], pr["Pi"], pr["phi"], seed=11, it=3, debug=True, time_phases=True)
-print("phase_ms", got["phase_ms"], "kernel_ms", got["sweep_kernel_ms"])
+print("phase_ms", got["phase_ms"], got["phase_ms_max"], "kernel_ms", got["sweep_kernel_ms"])
 steps = ref["lp"].shape[0]
 for st in range(min(steps, 4)):
     d = np.abs(got["lp"][st] - ref["lp"][st]).max()
