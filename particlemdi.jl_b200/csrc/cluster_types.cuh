@@ -113,6 +113,77 @@ __device__ __forceinline__ void gauss_add_block(const DsDev& ds, long long row, 
   if (lane == 0) ds.aux[row * ds.J + j] = acc;
 }
 
+// Fused cluster_add!(x_prev) + calc_logprob(x_cur) for the row a particle chose in the previous
+// step: the row is read once, updated, written back and evaluated against the next observation
+// in the same pass (same arithmetic as gauss_add_block followed by gauss_eval_block).
+__device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long row, int j, int n,
+                                                    const double* xp, const double* xc, int lane) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const double nn = (double)n;
+  const double c1 = __dadd_rn(__dadd_rn(nn, -1.0), 0.001);
+  const double c2 = __dmul_rn(2.0, __dadd_rn(nn, 0.001));
+  const double c3 = __dadd_rn(nn, 0.001);
+  const double c4 = __dmul_rn(__dadd_rn(__dmul_rn(0.5, nn), 0.5), c3);
+  const double c5 = __dadd_rn(nn, 1.001);
+  const double c6 = __dadd_rn(nn, 1.0);
+  const double r2 = __drcp_rn(c2), r3 = __drcp_rn(c3), r6 = __drcp_rn(c6);
+  const long long base = row * ds.Dp + q0 + 2 * lane;
+  double prodl = 1.0, prode = 1.0;
+#pragma unroll 1
+  for (int h = 0; h < 4; h += 2) {
+    double2 sm[2], bt[2], mu[2], ln[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (h + i < nit) {
+        const long long o = base + (h + i) * PMDI_WF;
+        sm[i] = ldcg_f64x2(ds.sum + o); bt[i] = ldcg_f64x2(ds.beta + o);
+        mu[i] = ldcg_f64x2(ds.mu + o); ln[i] = ldcg_f64x2(ds.lamn + o);
+      }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+      if (h + i < nit) {
+        const int qo = q0 + (h + i) * PMDI_WF + 2 * lane;
+        const long long o = base + (h + i) * PMDI_WF;
+        const double2 x = *(const double2*)(xp + qo);
+        const double2 y = *(const double2*)(xc + qo);
+        const uchar2 fl = *(const uchar2*)(ds.flag + qo);
+        if (fl.x) {
+          sm[i].x = __dadd_rn(sm[i].x, x.x);
+          const double dd = __dadd_rn(x.x, -mu[i].x);
+          bt[i].x = __dadd_rn(bt[i].x, div_const(__dmul_rn(c1, __dmul_rn(dd, dd)), c2, r2));
+          mu[i].x = div_const(sm[i].x, c3, r3);
+          ln[i].x = div_const(__ddiv_rn(c4, __dmul_rn(bt[i].x, c5)), c6, r6);
+          prodl *= ln[i].x;
+          const double d = y.x - mu[i].x;
+          prode *= fma(d * d, ln[i].x, 1.0);
+        }
+        if (fl.y) {
+          sm[i].y = __dadd_rn(sm[i].y, x.y);
+          const double dd = __dadd_rn(x.y, -mu[i].y);
+          bt[i].y = __dadd_rn(bt[i].y, div_const(__dmul_rn(c1, __dmul_rn(dd, dd)), c2, r2));
+          mu[i].y = div_const(sm[i].y, c3, r3);
+          ln[i].y = div_const(__ddiv_rn(c4, __dmul_rn(bt[i].y, c5)), c6, r6);
+          prodl *= ln[i].y;
+          const double d = y.y - mu[i].y;
+          prode *= fma(d * d, ln[i].y, 1.0);
+        }
+        *(double2*)(ds.sum + o) = sm[i];
+        *(double2*)(ds.beta + o) = bt[i];
+        *(double2*)(ds.mu + o) = mu[i];
+        *(double2*)(ds.lamn + o) = ln[i];
+      }
+  }
+  double a = 0.5 * log(prodl), e = log(prode);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(FULL, a, o);
+    e += __shfl_xor_sync(FULL, e, o);
+  }
+  if (lane == 0) ds.aux[row * ds.J + j] = a;
+  return a - (0.5 * nn + 1.0) * e;
+}
+
 // aux of a row from its stored state (used after the prefix build)
 __device__ __forceinline__ void gauss_aux_block(const DsDev& ds, long long row, int j, int lane) {
   const int q0 = j * PMDI_FB;

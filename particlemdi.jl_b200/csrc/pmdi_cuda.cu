@@ -87,7 +87,9 @@ struct pmdi_ctx {
   bool layout_dirty = true;
   // static layout
   std::vector<int> cta_off, cta_units;
-  int max_units = 0, sm_x_bytes = 0, lf_T = 0, sm_rowcap = 0, Jmax = 0;
+  int max_units = 0, sm_x_bytes = 0, lf_T = 0, lf_want = 0, item_cap = 0, Jmax = 0;
+  bool assigned = false;
+  std::vector<double> last_occ;
   size_t dyn_smem = 0;
   std::vector<double> lf_host;
   DevBuf<double> lf_dev;
@@ -173,10 +175,9 @@ int build_rc(pmdi_ctx* c, int k) {
   return 0;
 }
 
-// Static layout: shared-memory budget, log-factorial table, units -> CTAs (longest-processing-time
-// greedy on bytes per occupied row, so every CTA streams a similar number of bytes per step).
+// Static layout (per bound data): staging offsets, log-factorial table.
 int build_layout(pmdi_ctx* c) {
-  const int K = c->K, P = c->P, N = c->N;
+  const int K = c->K;
   for (int k = 0; k < K; ++k)
     if (!c->ds[k].bound) return fail(3, "pmdi: dataset " + std::to_string(k) + " is not bound");
   int off = 0, Jmax = 1;
@@ -184,23 +185,42 @@ int build_layout(pmdi_ctx* c) {
   for (int k = 0; k < K; ++k) {
     Dataset& s = c->ds[k];
     off = round_up(off, 16);
-    c->sp.ds[k].x_off = off;  // re-applied in fill (see below)
     off += s.Dp * (s.type == T_GAUSSIAN ? 8 : 4);
     Jmax = std::max(Jmax, s.J);
     if (s.type == T_NEGBINOM) nb_max_arg = std::max(nb_max_arg, s.max_arg);
   }
   c->sm_x_bytes = round_up(off, 16);
   c->Jmax = Jmax;
-  // units
+  c->lf_want = 0;
+  if (nb_max_arg >= 0) {
+    c->lf_want = (int)std::min<long long>(nb_max_arg + 2, 28000);
+    if (c->lf_want < 256) c->lf_want = 256;
+    c->lf_host.resize(c->lf_want);
+    for (int i = 0; i < c->lf_want; ++i) c->lf_host[i] = std::lgamma((double)i + 1.0);
+    CK(c->lf_dev.ensure(c->lf_want));
+    CK(cudaMemcpy(c->lf_dev.p, c->lf_host.data(), sizeof(double) * c->lf_want, cudaMemcpyHostToDevice));
+  }
+  c->layout_dirty = false;
+  c->assigned = false;
+  return 0;
+}
+
+// Units (dataset, particle slot) -> CTAs: longest-processing-time greedy on the bytes a unit streams
+// per observation step (occupied rows read + one row read-modify-written), so that every CTA moves a
+// similar number of bytes.  occ[k] = occupied labels expected for dataset k (from the prefix).
+// Then the shared-memory budget of the sweep kernel.
+int assign_units(pmdi_ctx* c, const double* occ) {
+  const int K = c->K, P = c->P, N = c->N, G = c->G;
   struct U { double cost; int k, slot; };
   std::vector<U> units;
   for (int k = 0; k < K; ++k) {
     const Dataset& s = c->ds[k];
-    const double w = s.type == T_GAUSSIAN ? 16.0 : (s.type == T_NEGBINOM ? 8.0 : 4.0);
-    for (int p = 0; p < P; ++p) units.push_back({w * s.Dp + 64.0, k, p});
+    const double rd = s.type == T_GAUSSIAN ? 16.0 : (s.type == T_NEGBINOM ? 8.0 : 4.0);
+    const double wr = s.type == T_GAUSSIAN ? 56.0 : (s.type == T_NEGBINOM ? 16.0 : 8.0);
+    const double cost = s.Dp * (rd * occ[k] + wr) + 2048.0;
+    for (int p = 0; p < P; ++p) units.push_back({cost, k, p});
   }
   std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
-  const int G = c->G;
   typedef std::pair<double, int> QE;
   std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
   for (int g = 0; g < G; ++g) pq.push({0.0, g});
@@ -220,34 +240,30 @@ int build_layout(pmdi_ctx* c) {
     c->max_units = std::max(c->max_units, (int)per[g].size());
   }
   c->cta_off[G] = (int)c->cta_units.size();
-  c->sm_rowcap = c->max_units * N;
+  // dynamic shared memory: 3 observation buffers | lf | proposal scratch | part+items | unit tables
   const int Npad = (N + 31) & ~31;
-  // fixed part of the dynamic shared memory: 2 observation buffers, proposal scratch, unit tables
-  const long long fixed = 2LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 +
-                          (long long)c->sm_rowcap * 4 + (4LL * c->max_units + 1) * 4;
-  // log-factorial table in shared memory (NegBinom only)
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  const long long budget = (long long)dev_smem - 4096 - fixed;
-  if (budget < 0) return fail(4, "pmdi: datasets too wide for the shared-memory observation staging");
-  c->lf_T = 0;
-  if (nb_max_arg >= 0) {
-    const long long want = nb_max_arg + 2, cap = budget / 8;
-    if (cap < 256) return fail(4, "pmdi: no shared memory left for the log-factorial table");
-    c->lf_T = (int)std::min(want, cap);
-    if (c->lf_T < 256) c->lf_T = 256;
-    c->lf_host.resize(c->lf_T);
-    for (int i = 0; i < c->lf_T; ++i) c->lf_host[i] = std::lgamma((double)i + 1.0);
-    CK(c->lf_dev.ensure(c->lf_T));
-    CK(cudaMemcpy(c->lf_dev.p, c->lf_host.data(), sizeof(double) * c->lf_T, cudaMemcpyHostToDevice));
-  }
-  c->dyn_smem = (size_t)fixed + (size_t)c->lf_T * 8;
+  const long long fixed = 3LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 +
+                          (long long)c->max_units * N * 4 + (6LL * c->max_units + 1) * 4 + 64;
+  const long long avail = (long long)dev_smem - 4096 - fixed;
+  const long long want_items = (long long)c->max_units * N * c->Jmax;
+  if (avail < 12LL * c->max_units * c->Jmax * 2)
+    return fail(4, "pmdi: datasets too wide / too many particles per SM for the shared-memory work queue");
+  long long items_b = std::min(want_items * 12, avail / 2);
+  const long long lf_b = std::min<long long>((long long)c->lf_want * 8, avail - items_b);
+  items_b = std::min(want_items * 12, avail - lf_b);
+  c->item_cap = (int)(items_b / 12);
+  c->lf_T = (int)(lf_b / 8);
+  if (c->lf_want > 0 && c->lf_T < 256) return fail(4, "pmdi: no shared memory left for the log-factorial table");
+  c->dyn_smem = (size_t)fixed + (size_t)c->lf_T * 8 + (size_t)c->item_cap * 12;
   CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
   CK(c->d_cta_off.ensure(c->cta_off.size()));
   CK(c->d_cta_units.ensure(c->cta_units.size()));
-  CK(cudaMemcpy(c->d_cta_off.p, c->cta_off.data(), sizeof(int) * c->cta_off.size(), cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(c->d_cta_units.p, c->cta_units.data(), sizeof(int) * c->cta_units.size(), cudaMemcpyHostToDevice));
-  c->layout_dirty = false;
+  CK(cudaMemcpyAsync(c->d_cta_off.p, c->cta_off.data(), sizeof(int) * c->cta_off.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaMemcpyAsync(c->d_cta_units.p, c->cta_units.data(), sizeof(int) * c->cta_units.size(), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  c->assigned = true;
   return 0;
 }
 
@@ -264,7 +280,7 @@ int fill_params(pmdi_ctx* c) {
   sp.Jmax = c->Jmax;
   sp.cta_off = c->d_cta_off.p; sp.cta_units = c->d_cta_units.p;
   sp.max_units = c->max_units; sp.sm_x_bytes = c->sm_x_bytes; sp.lf_T = c->lf_T;
-  sp.sm_rowcap = c->sm_rowcap; sp.lf_glob = c->lf_dev.p;
+  sp.item_cap = c->item_cap; sp.lf_glob = c->lf_dev.p;
   return 0;
 }
 
@@ -476,6 +492,26 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   if (K > 1 && !a->phi) return fail(1, "pmdi_sweep: phi is required when K > 1");
   const int steps = (int)(n - a->n1 + 1);
   SweepParams& sp = c->sp;
+  {  // occupied labels in the rho-prefix of every dataset -> byte cost of a unit -> CTA assignment
+    std::vector<double> occ(K, 1.0);
+    for (int k = 0; k < K; ++k) {
+      std::vector<uint8_t> seen_l(N + 1, 0);
+      int cnt = 0;
+      for (long long t = 0; t + 1 < a->n1; ++t) {
+        const int64_t o = a->order_obs[t];
+        if (o < 1 || o > n) break;
+        const int64_t l = a->s[(size_t)(o - 1) + (size_t)n * k];
+        if (l >= 1 && l <= N && !seen_l[l]) { seen_l[l] = 1; ++cnt; }
+      }
+      occ[k] = std::max(1, cnt) + 0.5;
+    }
+    if (!c->assigned || occ != c->last_occ) {
+      rc = assign_units(c, occ.data());
+      if (rc) return rc;
+      c->last_occ = occ;
+      fill_params(c);
+    }
+  }
   // validate + convert
   std::vector<int> order(n);
   std::vector<uint8_t> seen(n, 0);

@@ -74,7 +74,7 @@ struct SweepParams {
   const int* cta_off;
   const int* cta_units;   /* k << 24 | slot                                   */
   int max_units, sm_x_bytes;
-  int lf_T, sm_rowcap;
+  int lf_T, item_cap;   /* log-factorial entries in smem; capacity of the per-step item queue */
   const double* lf_glob;  /* log-factorial table [lf_T]                       */
   unsigned* bar;          /* grid barrier counter                             */
   int* err;

@@ -4,19 +4,23 @@
 // is owned by one CTA for the whole sweep, so predictive, proposal and add of a unit are
 // CTA-local; only the particle weights need the whole grid.
 //
-//   phase A  predictive      calc_logprob for every occupied cluster row of the CTA's units
-//                            (src/pmdi.jl:218-220) -> part[row][block]
-//   phase B  proposal        per owned unit: sum partials, softmax-cdf, draw, weight increment
-//                            (src/pmdi.jl:223-265) -> lab/inc[step parity][k][slot]
-//   phase C  cluster_add!    chosen row of every owned unit (src/pmdi.jl:275-310, dense form)
+// Per observation step a CTA runs ONE dynamically scheduled queue of work items
+// (unit, occupied row, 256-feature block), handed to warps through a shared-memory counter:
+//   * item        calc_logprob of the row block against the staged observation
+//                 (src/pmdi.jl:218-220); for the row the particle chose in the previous step the
+//                 item first applies the pending cluster_add! (src/pmdi.jl:300) in the same pass;
+//   * proposal    the warp that finishes the last item of a unit sums the unit's partials,
+//                 builds the softmax-cdf, draws the label and the weight increment
+//                 (src/pmdi.jl:223-265) -> lab/inc[step parity][k][slot], pending add;
 //   -- grid barrier --
-//   phase E  weights + ESS   every CTA folds all increments and the Phi coupling
-//                            (src/misc.jl:50-59) into its private copy of the log-weights and
-//                            evaluates calc_ESS (src/misc.jl:15-25): identical bits everywhere
-//   [resampling steps only]  CTA 0: draw_partstar (src/misc.jl:27-47) + copy plan; barrier;
-//                            all CTAs move the duplicated particles' rows; barrier
-//
-// The observation rows are prefetched one step ahead with cp.async into a double buffer.
+//   * weights     every CTA folds all increments and the Phi coupling (src/misc.jl:50-59) into
+//                 its private copy of the log-weights and evaluates calc_ESS (src/misc.jl:15-25):
+//                 identical bits everywhere, no second barrier;
+//   * resampling steps only: pending adds are flushed, CTA 0 runs draw_partstar
+//                 (src/misc.jl:27-47) + the copy plan; barrier; all CTAs move the duplicated
+//                 particles' rows; barrier.
+// Observation rows are prefetched one step ahead with cp.async into a 3-deep ring (the previous
+// row is still needed by the fused add).
 #pragma once
 #include "cluster_types.cuh"
 
@@ -26,6 +30,8 @@ struct SweepSmem {
   int total_items;
   int plan_drop;
   unsigned rows_eval[PMDI_MAX_K];
+  unsigned long long tacc[8];
+  unsigned long long t_prev;
 };
 
 // ---- block-wide helpers (fixed shapes -> identical bits in every CTA) -------------------------
@@ -168,7 +174,125 @@ __device__ __forceinline__ void cp_async_commit_wait_all() {
   asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
-extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepParams sp) {
+// per-CTA views into dynamic shared memory
+struct CtaTables {
+  unsigned* urow;   // [max_units][N]   occupied rows of a unit: label | n << 8
+  int* ucount;      // [max_units]      number of occupied rows
+  int* uoff;        // [max_units + 1]  first item of a unit in this step's queue
+  int* uinfo;       // [max_units]      k << 24 | slot
+  int* pend;        // [max_units]      pending add: label | n_after << 8, or -1
+  int* remaining;   // [max_units]      items of the unit not yet finished this step
+  unsigned* items;  // [item_cap]       u << 13 | e << 5 | j
+  double* part;     // [item_cap]       predictive partial sums of this step
+  double* lp_s;     // [NW][Npad]       per-warp proposal scratch
+};
+
+// Proposal for one unit (dataset k, particle slot), by one warp: src/pmdi.jl:223-265.
+__device__ __noinline__ void propose_unit(const SweepParams& sp, const CtaTables& T, int u, int step, int ev,
+                                          unsigned* rows_eval_s) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = sp.K, N = sp.N, P = sp.P, par = step & 1;
+  const int Npad = (N + 31) & ~31;
+  const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
+  const DsDev& ds = sp.ds[k];
+  const int p = ldcg_i32(sp.logical_of + (ev & 1) * P + slot);  // logical particle: RNG address, log index
+  const long long row0 = (long long)slot * N;
+  double* lps = T.lp_s + (size_t)warp * Npad;
+  const double lpe = sp.lp_empty[(size_t)step * K + k];
+  for (int m = lane; m < Npad; m += 32) lps[m] = lpe;
+  __syncwarp();
+  const int cnt = T.ucount[u];
+  const double* part = T.part + T.uoff[u];
+  for (int e = lane; e < cnt; e += 32) {
+    const unsigned ent = T.urow[(size_t)u * N + e];
+    double a = ds.rc[ent >> 8];
+    for (int j = 0; j < ds.J; ++j) a += part[e * ds.J + j];
+    lps[ent & 0xFF] = a;
+  }
+  __syncwarp();
+  double lpv[PMDI_MAX_N / 32];
+  double mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+    lpv[c] = -INFINITY;
+    if (c * 32 < N) {
+      const int m = c * 32 + lane;
+      if (m < N) {
+        lpv[c] = lps[m];
+        mx = fmax(mx, lpv[c]);
+        if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = lpv[c];
+      }
+    }
+  }
+  mx = warp_max(mx);
+  // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
+  double cv[PMDI_MAX_N / 32];
+  double run = 0.0;
+#pragma unroll
+  for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+    cv[c] = 0.0;
+    if (c * 32 < N) {
+      const int m = c * 32 + lane;
+      double f = 0.0;
+      if (m < N) f = exp(lpv[c] - mx) * sp.Pi[k * N + m];
+      const int lim = min(32, N - c * 32);
+#pragma unroll 1
+      for (int l = 0; l < lim; ++l) {
+        run += __shfl_sync(FULL, f, l);
+        if (lane == l) cv[c] = run;
+      }
+    }
+  }
+  const double tot = run;
+  const double inc = log(tot) + mx;
+  int label;
+  if (p == 0) {
+    label = (int)sp.s_in[(size_t)k * sp.n_obs + sp.order[sp.n1 - 1 + step]] - 1;  // reference trajectory (:262)
+  } else {
+    const double uu = sp.tape_alloc ? sp.tape_alloc[((size_t)step * K + k) * P + p]
+                                    : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
+    label = N - 1;
+    bool found = false;
+#pragma unroll
+    for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
+      if (c * 32 < N && !found) {
+        const int m = c * 32 + lane;
+        const bool hit = (m < N - 1) && (cv[c] / tot > uu);  // strict '>' (:255)
+        const unsigned b = __ballot_sync(FULL, hit);
+        if (b) { label = c * 32 + __ffs(b) - 1; found = true; }
+      }
+    }
+  }
+  // bookkeeping of the chosen row: size, occupied-row list, pending add
+  int pos = -1;
+  for (int e0 = 0; e0 < cnt; e0 += 32) {
+    const int e = e0 + lane;
+    const bool hit = (e < cnt) && ((int)(T.urow[(size_t)u * N + e] & 0xFF) == label);
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (b) { pos = e0 + __ffs(b) - 1; break; }
+  }
+  if (lane == 0) {
+    int n_new = 1;
+    if (pos >= 0) {
+      const unsigned ent = T.urow[(size_t)u * N + pos] + (1u << 8);
+      T.urow[(size_t)u * N + pos] = ent;
+      n_new = (int)(ent >> 8);
+    } else {
+      T.urow[(size_t)u * N + cnt] = (unsigned)label | (1u << 8);
+      T.ucount[u] = cnt + 1;
+    }
+    ds.n[row0 + label] = n_new;
+    T.pend[u] = label | (n_new << 8);
+    sp.lab[((size_t)par * K + k) * P + slot] = (uint8_t)label;
+    sp.inc[((size_t)par * K + k) * P + slot] = inc;
+    sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
+    if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
+    atomicAdd(&rows_eval_s[k], (unsigned)cnt);
+  }
+  __syncwarp();
+}
+
+extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_constant__ SweepParams sp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ SweepSmem sm;
   __shared__ int s_tmp[PMDI_NT + 2];
@@ -179,20 +303,24 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
   const int K = sp.K, N = sp.N, P = sp.P;
   const int Npad = (N + 31) & ~31;
 
-  // dynamic shared memory: [x buffer 0][x buffer 1][lf table][lp scratch NW x Npad][unit tables]
-  unsigned char* xbuf[2] = {smem_raw, smem_raw + sp.sm_x_bytes};
-  double* lf = (double*)(smem_raw + 2 * (size_t)sp.sm_x_bytes);
-  double* lp_s = lf + sp.lf_T;
-  unsigned* urow = (unsigned*)(lp_s + (size_t)NW * Npad);   // [nu][N]: label | n << 8
+  // dynamic shared memory: [3 x observation][lf table][lp scratch][part][items][unit tables]
+  unsigned char* xbuf[3] = {smem_raw, smem_raw + sp.sm_x_bytes, smem_raw + 2 * (size_t)sp.sm_x_bytes};
+  double* lf = (double*)(smem_raw + 3 * (size_t)sp.sm_x_bytes);
+  CtaTables T;
+  T.lp_s = lf + sp.lf_T;
+  T.part = T.lp_s + (size_t)NW * Npad;
+  T.items = (unsigned*)(T.part + sp.item_cap);
+  T.urow = T.items + sp.item_cap;
   const int u0 = sp.cta_off[cta], nu = sp.cta_off[cta + 1] - u0;
-  int* ucount = (int*)(urow + (size_t)sp.max_units * N);     // [max_units]
-  int* uoff = ucount + sp.max_units;                         // [max_units + 1]
-  int* uinfo = uoff + sp.max_units + 1;                      // [max_units] k << 24 | slot
-  int* ulab = uinfo + sp.max_units;                          // [max_units] label chosen this step
+  T.ucount = (int*)(T.urow + (size_t)sp.max_units * N);
+  T.uoff = T.ucount + sp.max_units;
+  T.uinfo = T.uoff + sp.max_units + 1;
+  T.pend = T.uinfo + sp.max_units;
+  T.remaining = T.pend + sp.max_units;
   const int lfT = sp.lf_T;
   for (int i = tid; i < lfT; i += PMDI_NT) lf[i] = sp.lf_glob[i];
   if (tid < PMDI_MAX_K) sm.rows_eval[tid] = 0;
-  for (int u = tid; u < nu; u += PMDI_NT) uinfo[u] = sp.cta_units[u0 + u];
+  for (int u = tid; u < nu; u += PMDI_NT) { T.uinfo[u] = sp.cta_units[u0 + u]; T.pend[u] = -1; }
 
   double* lw = sp.lw + (size_t)cta * P;  // private copy, thread t owns p = t, t + NT, ...
   for (int p = tid; p < P; p += PMDI_NT) lw[p] = sp.lw_init;
@@ -200,31 +328,33 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
   unsigned epoch = 0;
   int ev = 0;
   const bool timing = sp.phase_ns != nullptr && tid == 0;
-  unsigned long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_prev = 0;
-  if (timing) t_prev = globaltimer_ns();
+  if (timing) {
+    for (int i = 0; i < 8; ++i) sm.tacc[i] = 0;
+    sm.t_prev = globaltimer_ns();
+  }
 #define PHASE_MARK(i_)                                   \
   if (timing) {                                          \
     const unsigned long long now_ = globaltimer_ns();    \
-    tacc[i_] += now_ - t_prev;                           \
-    t_prev = now_;                                       \
+    sm.tacc[i_] += now_ - sm.t_prev;                     \
+    sm.t_prev = now_;                                    \
   }
 
   // occupied rows of every owned unit, from the statistics in HBM
   auto rebuild_rows = [&]() {
     for (int u = warp; u < nu; u += NW) {
-      const int k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
+      const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
       int cnt = 0;
       for (int m0 = 0; m0 < N; m0 += 32) {
         const int m = m0 + lane;
         const int nm = (m < N) ? ldcg_i32(sp.ds[k].n + (long long)slot * N + m) : 0;
         const unsigned b = __ballot_sync(FULL, nm > 0);
-        if (nm > 0) urow[(size_t)u * N + cnt + __popc(b & ((1u << lane) - 1))] = (unsigned)m | ((unsigned)nm << 8);
+        if (nm > 0) T.urow[(size_t)u * N + cnt + __popc(b & ((1u << lane) - 1))] = (unsigned)m | ((unsigned)nm << 8);
         cnt += __popc(b);
       }
-      if (lane == 0) ucount[u] = cnt;
+      if (lane == 0) T.ucount[u] = cnt;
     }
   };
-  // stage (asynchronously) the observation of one step into buffer b
+  // stage (asynchronously) the observation of one step into ring buffer b
   auto prefetch_obs = [&](int step, int b) {
     if (step >= sp.steps) return;
     const int obs = sp.order[sp.n1 - 1 + step];
@@ -236,6 +366,22 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
       for (int o = tid * 16; o < bytes; o += PMDI_NT * 16) cp_async16(dst + o, src + o);
     }
   };
+  // cluster_add! of the pending row of every unit, against observation buffer xb (resampling steps)
+  auto flush_adds = [&](const unsigned char* xb) {
+    for (int it = warp; it < nu * sp.Jmax; it += NW) {
+      const int u = it / sp.Jmax, j = it - u * sp.Jmax;
+      const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
+      const DsDev& ds = sp.ds[k];
+      if (j >= ds.J || T.pend[u] < 0) continue;
+      const int label = T.pend[u] & 0xFF, n = T.pend[u] >> 8;
+      const long long row = (long long)slot * N + label;
+      if (ds.type == T_GAUSSIAN) gauss_add_block(ds, row, j, n, (const double*)(xb + ds.x_off), lane);
+      else if (ds.type == T_CATEGORICAL) cat_add_block(ds, row, j, (const int*)(xb + ds.x_off), lane);
+      else nb_add_block(ds, row, j, n, (const int*)(xb + ds.x_off), lane, lf, lfT);
+    }
+    __syncthreads();
+    for (int u = tid; u < nu; u += PMDI_NT) T.pend[u] = -1;
+  };
 
   __syncthreads();  // uinfo is visible to every warp
   rebuild_rows();
@@ -243,182 +389,99 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
 
   for (int step = 0; step < sp.steps; ++step) {
     const int par = step & 1;
-    const unsigned char* xs_raw = xbuf[par];
-    const int* logi_cur = sp.logical_of + (ev & 1) * P;
+    const unsigned char* xs_cur = xbuf[step % 3];
+    const unsigned char* xs_prev = xbuf[(step + 2) % 3];
     const int* slot_cur = sp.slot_of + (ev & 1) * P;
-    uint8_t* lab_g = sp.lab + (size_t)par * K * P;
-    double* inc_g = sp.inc + (size_t)par * K * P;
+    const uint8_t* lab_g = sp.lab + (size_t)par * K * P;
+    const double* inc_g = sp.inc + (size_t)par * K * P;
 
     cp_async_commit_wait_all();   // this step's observation has landed (own copies)
-    __syncthreads();              // ... everybody's; previous step's add is complete too
-    prefetch_obs(step + 1, par ^ 1);
+    __syncthreads();              // ... everybody's; last step's row lists are complete
+    prefetch_obs(step + 1, (step + 1) % 3);
     if (warp == 0) {  // item offsets of the units: uoff[u] = sum_{v<u} ucount[v] * J_v
       int run = 0;
       for (int ub = 0; ub < nu; ub += 32) {
         const int u = ub + lane;
         int c = 0;
-        if (u < nu) c = ucount[u] * sp.ds[uinfo[u] >> 24].J;
+        if (u < nu) c = T.ucount[u] * sp.ds[T.uinfo[u] >> 24].J;
         int inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           const int v = __shfl_up_sync(FULL, inc, o);
           if (lane >= o) inc += v;
         }
-        if (u < nu) uoff[u] = run + inc - c;
+        if (u < nu) { T.uoff[u] = run + inc - c; T.remaining[u] = c; }
         run += __shfl_sync(FULL, inc, 31);
       }
-      if (lane == 0) { uoff[nu] = run; sm.total_items = run; sm.item_ctr = 0; }
+      if (lane == 0) {
+        T.uoff[nu] = run;
+        sm.total_items = run;
+        sm.item_ctr = 0;
+        if (run > sp.item_cap) atomicExch(sp.err, 78);
+      }
+    }
+    __syncthreads();
+    const int total = sm.total_items;
+    if (total > sp.item_cap) return;  // every CTA sees err through the barrier watchdog
+    for (int it = tid; it < total; it += PMDI_NT) {  // decode table: item -> (unit, row entry, block)
+      int lo = 0, hi = nu - 1;  // last u with uoff[u] <= it
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (T.uoff[mid] <= it) lo = mid; else hi = mid - 1;
+      }
+      const int J = sp.ds[T.uinfo[lo] >> 24].J;
+      const int r = it - T.uoff[lo];
+      const int e = r / J;
+      T.items[it] = ((unsigned)lo << 13) | ((unsigned)e << 5) | (unsigned)(r - e * J);
     }
     __syncthreads();
     PHASE_MARK(0)
-    // ------------------------------------------------------------------ phase A: predictive
-    {
-      const int total = sm.total_items;
-      for (;;) {
-        int it = 0;
-        if (lane == 0) it = atomicAdd(&sm.item_ctr, 1);
-        it = __shfl_sync(FULL, it, 0);
-        if (it >= total) break;
-        int lo = 0, hi = nu - 1;  // last u with uoff[u] <= it
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (uoff[mid] <= it) lo = mid; else hi = mid - 1;
-        }
-        const int u = lo, k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
-        const DsDev& ds = sp.ds[k];
-        const int r = it - uoff[u];
-        const int e = r / ds.J, j = r - e * ds.J;
-        const unsigned ent = urow[(size_t)u * N + e];
-        const int m = ent & 0xFF, n = ent >> 8;
-        const long long row = (long long)slot * N + m;
-        double v;
-        if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, n, (const double*)(xs_raw + ds.x_off), lane);
-        else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)(xs_raw + ds.x_off), lane);
-        else v = nb_eval_block(ds, row, j, n, (const int*)(xs_raw + ds.x_off), lane, lf, lfT);
-        if (lane == 0) ds.part[row * ds.J + j] = v;
-      }
-    }
-    __syncthreads();
-    PHASE_MARK(1)
-    // ------------------------------------------------------------------ phase B: proposal
-    for (int u = warp; u < nu; u += NW) {
-      const int k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
+    // ------------------------------------------------------------------ the item queue
+    for (;;) {
+      int it = 0;
+      if (lane == 0) it = atomicAdd(&sm.item_ctr, 1);
+      it = __shfl_sync(FULL, it, 0);
+      if (it >= total) break;
+      const unsigned code = T.items[it];
+      const int u = code >> 13, e = (code >> 5) & 0xFF, j = code & 31;
+      const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
       const DsDev& ds = sp.ds[k];
-      const int p = ldcg_i32(logi_cur + slot);  // logical particle (RNG address, trajectory log)
-      const long long row0 = (long long)slot * N;
-      double* lps = lp_s + (size_t)warp * Npad;
-      const double lpe = sp.lp_empty[(size_t)step * K + k];
-      for (int m = lane; m < Npad; m += 32) lps[m] = lpe;
-      __syncwarp();
-      const int cnt = ucount[u];
-      for (int e = lane; e < cnt; e += 32) {
-        const unsigned ent = urow[(size_t)u * N + e];
-        const int m = ent & 0xFF, nm = ent >> 8;
-        const double* pp = ds.part + (row0 + m) * ds.J;
-        double a = ds.rc[nm];
-        for (int j0 = 0; j0 < ds.J; j0 += 8) {
-          double v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = (j0 + j < ds.J) ? __ldcg(pp + j0 + j) : 0.0;
-#pragma unroll
-          for (int j = 0; j < 8; ++j) if (j0 + j < ds.J) a += v[j];
-        }
-        lps[m] = a;
-      }
-      __syncwarp();
-      double lpv[PMDI_MAX_N / 32];
-      double mx = -INFINITY;
-#pragma unroll
-      for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
-        lpv[c] = -INFINITY;
-        if (c * 32 < N) {
-          const int m = c * 32 + lane;
-          if (m < N) {
-            lpv[c] = lps[m];
-            mx = fmax(mx, lpv[c]);
-            if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = lpv[c];
-          }
-        }
-      }
-      mx = warp_max(mx);
-      // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
-      double cv[PMDI_MAX_N / 32];
-      double run = 0.0;
-#pragma unroll
-      for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
-        cv[c] = 0.0;
-        if (c * 32 < N) {
-          const int m = c * 32 + lane;
-          double f = 0.0;
-          if (m < N) f = exp(lpv[c] - mx) * sp.Pi[k * N + m];
-          const int lim = min(32, N - c * 32);
-#pragma unroll 1
-          for (int l = 0; l < lim; ++l) {
-            run += __shfl_sync(FULL, f, l);
-            if (lane == l) cv[c] = run;
-          }
-        }
-      }
-      const double tot = run;
-      const double inc = log(tot) + mx;
-      int label;
-      if (p == 0) {
-        label = (int)sp.s_in[(size_t)k * sp.n_obs + sp.order[sp.n1 - 1 + step]] - 1;  // reference trajectory (:262)
+      const unsigned ent = T.urow[(size_t)u * N + e];
+      const int m = ent & 0xFF, n = ent >> 8;
+      const long long row = (long long)slot * N + m;
+      const int pd = T.pend[u];
+      const bool fused = (pd >= 0) && ((pd & 0xFF) == m);  // pending add of the previous step (n == pd >> 8)
+      double v;
+      if (ds.type == T_GAUSSIAN) {
+        if (fused) v = gauss_fused_block(ds, row, j, n, (const double*)(xs_prev + ds.x_off),
+                                         (const double*)(xs_cur + ds.x_off), lane);
+        else v = gauss_eval_block(ds, row, j, n, (const double*)(xs_cur + ds.x_off), lane);
+      } else if (ds.type == T_CATEGORICAL) {
+        if (fused) { cat_add_block(ds, row, j, (const int*)(xs_prev + ds.x_off), lane); __syncwarp(); }
+        v = cat_eval_block(ds, row, j, (const int*)(xs_cur + ds.x_off), lane);
       } else {
-        const double uu = sp.tape_alloc ? sp.tape_alloc[((size_t)step * K + k) * P + p]
-                                        : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
-        label = N - 1;
-        bool found = false;
-#pragma unroll
-        for (int c = 0; c < PMDI_MAX_N / 32; ++c) {
-          if (c * 32 < N && !found) {
-            const int m = c * 32 + lane;
-            const bool hit = (m < N - 1) && (cv[c] / tot > uu);  // strict '>' (:255)
-            const unsigned b = __ballot_sync(FULL, hit);
-            if (b) { label = c * 32 + __ffs(b) - 1; found = true; }
-          }
-        }
+        if (fused) { nb_add_block(ds, row, j, n, (const int*)(xs_prev + ds.x_off), lane, lf, lfT); __syncwarp(); }
+        v = nb_eval_block(ds, row, j, n, (const int*)(xs_cur + ds.x_off), lane, lf, lfT);
       }
-      // bookkeeping of the chosen row: size, occupied-row list
-      int pos = -1;
-      for (int e0 = 0; e0 < cnt; e0 += 32) {
-        const int e = e0 + lane;
-        const bool hit = (e < cnt) && ((int)(urow[(size_t)u * N + e] & 0xFF) == label);
-        const unsigned b = __ballot_sync(FULL, hit);
-        if (b) { pos = e0 + __ffs(b) - 1; break; }
-      }
+      int last = 0;
       if (lane == 0) {
-        if (pos >= 0) urow[(size_t)u * N + pos] += (1u << 8);
-        else { urow[(size_t)u * N + cnt] = (unsigned)label | (1u << 8); ucount[u] = cnt + 1; }
-        const int n_new = (pos >= 0 ? (int)(urow[(size_t)u * N + pos] >> 8) : 1);
-        ds.n[row0 + label] = n_new;
-        ulab[u] = label | (n_new << 8);
-        lab_g[(size_t)k * P + slot] = (uint8_t)label;
-        inc_g[(size_t)k * P + slot] = inc;
-        sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
-        if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
-        atomicAdd(&sm.rows_eval[k], (unsigned)cnt);
+        T.part[it] = v;
+        __threadfence_block();
+        last = (atomicSub(&T.remaining[u], 1) == 1);
+      }
+      last = __shfl_sync(FULL, last, 0);
+      if (last) {  // this warp finished the unit: run its proposal now
+        __threadfence_block();
+        propose_unit(sp, T, u, step, ev, sm.rows_eval);
       }
     }
-    __syncthreads();
-    PHASE_MARK(2)
-    // ------------------------------------------------------------------ phase C: cluster_add!
-    for (int it = warp; it < nu * sp.Jmax; it += NW) {
-      const int u = it / sp.Jmax, j = it - u * sp.Jmax;
-      const int k = uinfo[u] >> 24, slot = uinfo[u] & 0xFFFFFF;
-      const DsDev& ds = sp.ds[k];
-      if (j >= ds.J) continue;
-      const int label = ulab[u] & 0xFF, n = ulab[u] >> 8;  // n = size after the add
-      const long long row = (long long)slot * N + label;
-      if (ds.type == T_GAUSSIAN) gauss_add_block(ds, row, j, n, (const double*)(xs_raw + ds.x_off), lane);
-      else if (ds.type == T_CATEGORICAL) cat_add_block(ds, row, j, (const int*)(xs_raw + ds.x_off), lane);
-      else nb_add_block(ds, row, j, n, (const int*)(xs_raw + ds.x_off), lane, lf, lfT);
-    }
-    PHASE_MARK(3)
+    for (int u = warp; u < nu; u += NW)  // units with no occupied row at all
+      if (T.uoff[u + 1] == T.uoff[u]) propose_unit(sp, T, u, step, ev, sm.rows_eval);
+    PHASE_MARK(1)
     if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
     PHASE_MARK(4)
 
-    // ------------------------------------------------------------------ phase E: weights + ESS
+    // ------------------------------------------------------------------ weights + ESS
     double mx = -INFINITY;
     for (int p = tid; p < P; p += PMDI_NT) {
       const int slot = ldcg_i32(slot_cur + p);
@@ -456,6 +519,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
     PHASE_MARK(5)
 
     if (do_res) {
+      flush_adds(xs_cur);
       if (cta == 0) resample_plan(sp, step, ev, mx, lw, s_tmp);
       if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
       const int ncopy = ldcg_i32(sp.plan_out);
@@ -479,7 +543,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const SweepPara
   if (cta == 0)
     for (int p = tid; p < P; p += PMDI_NT) sp.lw_out[p] = lw[p];
   if (timing)
-    for (int i = 0; i < 8; ++i) sp.phase_ns[(size_t)cta * 8 + i] = tacc[i];
+    for (int i = 0; i < 8; ++i) sp.phase_ns[(size_t)cta * 8 + i] = sm.tacc[i];
   if (cta == 0 && tid == 0) sp.counters[2] = ev;
 #undef PHASE_MARK
 }
