@@ -11,6 +11,8 @@
 #pragma once
 #include "device_utils.cuh"
 
+#define PMDI_QB 4 /* 256-feature blocks per work item */
+
 // ------------------------------------------------------------------------------------------
 // Gaussian — reference src/datatypes/gaussian_cluster.jl:37-52 (calc_logprob), :54-66 (cluster_add!)
 //   log p = nflag*rc_n + sum_q flag_q [ 0.5 log(lam_q/(n+1)) - (n/2+1) log(1 + (x_q-mu_q)^2 lam_q/(n+1)) ]
@@ -116,10 +118,10 @@ __device__ __forceinline__ void gauss_add_block(const DsDev& ds, long long row, 
 // Fused cluster_add!(x_prev) + calc_logprob(x_cur) for the row a particle chose in the previous
 // step: the row is read once, updated, written back and evaluated against the next observation
 // in the same pass (same arithmetic as gauss_add_block followed by gauss_eval_block).
-__device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long row, int j, int n,
-                                                    const double* xp, const double* xc, int lane) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+// (noinline with by-value arguments: its register allocation stays out of the item loop)
+__device__ __noinline__ double gauss_fused_raw(double* sum_p, double* beta_p, double* mu_p, double* lamn_p,
+                                               double* aux_p, const uint8_t* flag_p, int nit, int n,
+                                               const double* xp, const double* xc, int lane) {
   const double nn = (double)n;
   const double c1 = __dadd_rn(__dadd_rn(nn, -1.0), 0.001);
   const double c2 = __dmul_rn(2.0, __dadd_rn(nn, 0.001));
@@ -128,7 +130,6 @@ __device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long r
   const double c5 = __dadd_rn(nn, 1.001);
   const double c6 = __dadd_rn(nn, 1.0);
   const double r2 = __drcp_rn(c2), r3 = __drcp_rn(c3), r6 = __drcp_rn(c6);
-  const long long base = row * ds.Dp + q0 + 2 * lane;
   double prodl = 1.0, prode = 1.0;
 #pragma unroll 1
   for (int h = 0; h < 4; h += 2) {
@@ -136,18 +137,17 @@ __device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long r
 #pragma unroll
     for (int i = 0; i < 2; ++i)
       if (h + i < nit) {
-        const long long o = base + (h + i) * PMDI_WF;
-        sm[i] = ldcg_f64x2(ds.sum + o); bt[i] = ldcg_f64x2(ds.beta + o);
-        mu[i] = ldcg_f64x2(ds.mu + o); ln[i] = ldcg_f64x2(ds.lamn + o);
+        const int o = (h + i) * PMDI_WF;
+        sm[i] = ldcg_f64x2(sum_p + o); bt[i] = ldcg_f64x2(beta_p + o);
+        mu[i] = ldcg_f64x2(mu_p + o); ln[i] = ldcg_f64x2(lamn_p + o);
       }
 #pragma unroll
     for (int i = 0; i < 2; ++i)
       if (h + i < nit) {
-        const int qo = q0 + (h + i) * PMDI_WF + 2 * lane;
-        const long long o = base + (h + i) * PMDI_WF;
-        const double2 x = *(const double2*)(xp + qo);
-        const double2 y = *(const double2*)(xc + qo);
-        const uchar2 fl = *(const uchar2*)(ds.flag + qo);
+        const int o = (h + i) * PMDI_WF;
+        const double2 x = *(const double2*)(xp + o);
+        const double2 y = *(const double2*)(xc + o);
+        const uchar2 fl = *(const uchar2*)(flag_p + o);
         if (fl.x) {
           sm[i].x = __dadd_rn(sm[i].x, x.x);
           const double dd = __dadd_rn(x.x, -mu[i].x);
@@ -168,10 +168,10 @@ __device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long r
           const double d = y.y - mu[i].y;
           prode *= fma(d * d, ln[i].y, 1.0);
         }
-        *(double2*)(ds.sum + o) = sm[i];
-        *(double2*)(ds.beta + o) = bt[i];
-        *(double2*)(ds.mu + o) = mu[i];
-        *(double2*)(ds.lamn + o) = ln[i];
+        *(double2*)(sum_p + o) = sm[i];
+        *(double2*)(beta_p + o) = bt[i];
+        *(double2*)(mu_p + o) = mu[i];
+        *(double2*)(lamn_p + o) = ln[i];
       }
   }
   double a = 0.5 * log(prodl), e = log(prode);
@@ -180,8 +180,16 @@ __device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long r
     a += __shfl_xor_sync(FULL, a, o);
     e += __shfl_xor_sync(FULL, e, o);
   }
-  if (lane == 0) ds.aux[row * ds.J + j] = a;
+  if (lane == 0) *aux_p = a;
   return a - (0.5 * nn + 1.0) * e;
+}
+__device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long row, int j, int n,
+                                                    const double* xp, const double* xc, int lane) {
+  const int q0 = j * PMDI_FB;
+  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const long long o = row * ds.Dp + q0 + 2 * lane;
+  return gauss_fused_raw(ds.sum + o, ds.beta + o, ds.mu + o, ds.lamn + o, ds.aux + row * ds.J + j,
+                         ds.flag + q0 + 2 * lane, nit, n, xp + q0 + 2 * lane, xc + q0 + 2 * lane, lane);
 }
 
 // aux of a row from its stored state (used after the prefix build)
@@ -301,6 +309,180 @@ __device__ __forceinline__ void nb_aux_block(const DsDev& ds, long long row, int
   }
   acc = warp_sum(acc);
   if (lane == 0) ds.aux[row * ds.J + j] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Work items of the sweep: up to PMDI_QB consecutive 256-feature blocks [j0, j1) of one row, by
+// one warp.  Loads run as a ROLLING prefetch four 64-feature iterations ahead: four named
+// register slots are refilled one by one as they are consumed, so 6-8 128-bit loads per lane stay
+// in flight for the whole item.  The x-independent aux terms are fetched by the first lanes at the
+// start and the warp reduces once per item.  The evaluators are separate (noinline) functions
+// with by-value arguments so that their prefetch registers are allocated independently of the
+// persistent kernel's state; the staged observation is read with explicit ld.shared.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double2 lds_f64x2(unsigned a) {
+  double2 v;
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ int2 lds_i32x2(unsigned a) {
+  int2 v;
+  asm("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ double lds_f64(unsigned a) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+  return v;
+}
+
+// mu / lm / flag / xs point at this lane's first feature of the item; nits 64-feature iterations.
+__device__ __noinline__ double gauss_eval_raw(const double* mu, const double* lm, const double* aux,
+                                              const uint8_t* flag /* NULL: all on */, unsigned xs, int nits,
+                                              int naux, int n, int lane) {
+  double a = (lane < naux) ? ldcg_f64(aux + lane) : 0.0;
+  double2 m0, m1, m2, m3, l0, l1, l2, l3;
+  m0 = m1 = m2 = m3 = l0 = l1 = l2 = l3 = make_double2(0.0, 0.0);
+  if (0 < nits) { m0 = ldcg_f64x2(mu); l0 = ldcg_f64x2(lm); }
+  if (1 < nits) { m1 = ldcg_f64x2(mu + PMDI_WF); l1 = ldcg_f64x2(lm + PMDI_WF); }
+  if (2 < nits) { m2 = ldcg_f64x2(mu + 2 * PMDI_WF); l2 = ldcg_f64x2(lm + 2 * PMDI_WF); }
+  if (3 < nits) { m3 = ldcg_f64x2(mu + 3 * PMDI_WF); l3 = ldcg_f64x2(lm + 3 * PMDI_WF); }
+  double acc = 0.0;
+#define PMDI_G_STEP(M, L, IT)                                                         \
+  if (i0 + IT < nits) {                                                               \
+    const double2 x = lds_f64x2(xs + (IT) * PMDI_WF * 8);                             \
+    const double d0 = x.x - M.x, d1 = x.y - M.y;                                      \
+    double f0 = fma(d0 * d0, L.x, 1.0), f1 = fma(d1 * d1, L.y, 1.0);                  \
+    if (flag) {                                                                       \
+      const uchar2 fl = *(const uchar2*)(flag + (IT) * PMDI_WF);                      \
+      f0 = fl.x ? f0 : 1.0;                                                           \
+      f1 = fl.y ? f1 : 1.0;                                                           \
+    }                                                                                 \
+    prod *= f0 * f1;                                                                  \
+    if (i0 + IT + 4 < nits) {                                                         \
+      M = ldcg_f64x2(mu + (IT + 4) * PMDI_WF);                                        \
+      L = ldcg_f64x2(lm + (IT + 4) * PMDI_WF);                                        \
+    }                                                                                 \
+  }
+  for (int i0 = 0; i0 < nits; i0 += 4) {
+    double prod = 1.0;
+    PMDI_G_STEP(m0, l0, 0)
+    PMDI_G_STEP(m1, l1, 1)
+    PMDI_G_STEP(m2, l2, 2)
+    PMDI_G_STEP(m3, l3, 3)
+    acc += log(prod);
+    mu += PMDI_FB; lm += PMDI_FB; xs += PMDI_FB * 8;
+    if (flag) flag += PMDI_FB;
+  }
+#undef PMDI_G_STEP
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(FULL, a, o);
+    acc += __shfl_xor_sync(FULL, acc, o);
+  }
+  return a - (0.5 * (double)n + 1.0) * acc;
+}
+__device__ __forceinline__ double gauss_eval_item(const DsDev& ds, long long row, int j0, int j1, int n,
+                                                  const double* xs, int lane) {
+  const int base = j0 * PMDI_FB + 2 * lane;
+  const int nits = (min(ds.Dp, j1 * PMDI_FB) - j0 * PMDI_FB) / PMDI_WF;
+  return gauss_eval_raw(ds.mu + row * ds.Dp + base, ds.lamn + row * ds.Dp + base, ds.aux + row * ds.J + j0,
+                        ds.all_on ? nullptr : ds.flag + base,
+                        (unsigned)__cvta_generic_to_shared(xs + base), nits, j1 - j0, n, lane);
+}
+
+// log-factorial with the table in shared memory (address lf_s), Stirling beyond T
+__device__ __forceinline__ double lfact_s(long long k, unsigned lf_s, int T) {
+  if (k < (long long)T) return lds_f64(lf_s + (unsigned)k * 8u);
+  const double z = (double)k + 1.0;
+  const double zi = 1.0 / z, zi2 = zi * zi;
+  return (z - 0.5) * log(z) - z + 0.91893853320467274178 +
+         zi * (1.0 / 12.0 - zi2 * (1.0 / 360.0 - zi2 * (1.0 / 1260.0)));
+}
+
+__device__ __noinline__ double nb_eval_raw(const long long* S, const double* aux, unsigned xs, int nits,
+                                           int naux, int n, unsigned lf_s, int T, int lane) {
+  double a = (lane < naux) ? ldcg_f64(aux + lane) : 0.0;
+  longlong2 s0, s1, s2, s3;
+  s0 = s1 = s2 = s3 = make_longlong2(0, 0);
+  if (0 < nits) s0 = ldcg_i64x2(S);
+  if (1 < nits) s1 = ldcg_i64x2(S + PMDI_WF);
+  if (2 < nits) s2 = ldcg_i64x2(S + 2 * PMDI_WF);
+  if (3 < nits) s3 = ldcg_i64x2(S + 3 * PMDI_WF);
+  double acc = 0.0;
+  const long long n2 = n + 2;
+#define PMDI_NB_STEP(SS, IT)                                                                            \
+  if (i0 + IT < nits) {                                                                                 \
+    const int2 x = lds_i32x2(xs + (IT) * PMDI_WF * 4);                                                  \
+    if (x.x >= 0) { const long long b = SS.x + x.x; acc += lfact_s(b, lf_s, T) - lfact_s(b + n2, lf_s, T); } \
+    if (x.y >= 0) { const long long b = SS.y + x.y; acc += lfact_s(b, lf_s, T) - lfact_s(b + n2, lf_s, T); } \
+    if (i0 + IT + 4 < nits) SS = ldcg_i64x2(S + (IT + 4) * PMDI_WF);                                    \
+  }
+  for (int i0 = 0; i0 < nits; i0 += 4) {
+    PMDI_NB_STEP(s0, 0)
+    PMDI_NB_STEP(s1, 1)
+    PMDI_NB_STEP(s2, 2)
+    PMDI_NB_STEP(s3, 3)
+    S += PMDI_FB; xs += PMDI_FB * 4;
+  }
+#undef PMDI_NB_STEP
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(FULL, a, o);
+    acc += __shfl_xor_sync(FULL, acc, o);
+  }
+  return a + acc;
+}
+__device__ __forceinline__ double nb_eval_item(const DsDev& ds, long long row, int j0, int j1, int n,
+                                               const int* xs, int lane, const double* lf, int T) {
+  const int base = j0 * PMDI_FB + 2 * lane;
+  const int nits = (min(ds.Dp, j1 * PMDI_FB) - j0 * PMDI_FB) / PMDI_WF;
+  return nb_eval_raw(ds.S + row * ds.Dp + base, ds.aux + row * ds.J + j0,
+                     (unsigned)__cvta_generic_to_shared(xs + base), nits, j1 - j0, n,
+                     (unsigned)__cvta_generic_to_shared(lf), T, lane);
+}
+
+__device__ __noinline__ double cat_eval_raw(const uint32_t* cnt, long long Dp, unsigned xs, int nits, int lane) {
+  unsigned a0 = 0, a1 = 0, a2 = 0, a3 = 0, b0 = 0, b1 = 0, b2 = 0, b3 = 0;
+  int2 v0, v1, v2, v3;
+  v0 = v1 = v2 = v3 = make_int2(0, 0);
+#define PMDI_C_LOAD(V, A, B, IT)                                                            \
+  {                                                                                         \
+    V = lds_i32x2(xs + (IT) * PMDI_WF * 4);                                                 \
+    A = V.x ? ldcg_u32(cnt + (long long)(V.x - 1) * Dp + (IT) * PMDI_WF) : 0u;              \
+    B = V.y ? ldcg_u32(cnt + (long long)(V.y - 1) * Dp + (IT) * PMDI_WF + 1) : 0u;          \
+  }
+  if (0 < nits) PMDI_C_LOAD(v0, a0, b0, 0)
+  if (1 < nits) PMDI_C_LOAD(v1, a1, b1, 1)
+  if (2 < nits) PMDI_C_LOAD(v2, a2, b2, 2)
+  if (3 < nits) PMDI_C_LOAD(v3, a3, b3, 3)
+  double acc = 0.0;
+#define PMDI_C_STEP(V, A, B, IT)                                                            \
+  if (i0 + IT < nits) {                                                                     \
+    const double f0 = V.x ? 0.5 + (double)A : 1.0;                                          \
+    const double f1 = V.y ? 0.5 + (double)B : 1.0;                                          \
+    prod *= f0 * f1;                                                                        \
+    if (i0 + IT + 4 < nits) PMDI_C_LOAD(V, A, B, IT + 4)                                    \
+  }
+  for (int i0 = 0; i0 < nits; i0 += 4) {
+    double prod = 1.0;
+    PMDI_C_STEP(v0, a0, b0, 0)
+    PMDI_C_STEP(v1, a1, b1, 1)
+    PMDI_C_STEP(v2, a2, b2, 2)
+    PMDI_C_STEP(v3, a3, b3, 3)
+    acc += log(prod);
+    cnt += PMDI_FB; xs += PMDI_FB * 4;
+  }
+#undef PMDI_C_STEP
+#undef PMDI_C_LOAD
+  return warp_sum(acc);
+}
+__device__ __forceinline__ double cat_eval_item(const DsDev& ds, long long row, int j0, int j1,
+                                                const int* xs, int lane) {
+  const int base = j0 * PMDI_FB + 2 * lane;
+  const int nits = (min(ds.Dp, j1 * PMDI_FB) - j0 * PMDI_FB) / PMDI_WF;
+  return cat_eval_raw(ds.cnt + row * (long long)ds.Lmax * ds.Dp + base, (long long)ds.Dp,
+                      (unsigned)__cvta_generic_to_shared(xs + base), nits, lane);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <queue>
 #include <string>
@@ -104,7 +105,7 @@ struct pmdi_ctx {
   DevBuf<uint8_t> lab, alloc_log;
   DevBuf<int2> copies;
   DevBuf<unsigned> bar;
-  DevBuf<unsigned long long> rows_eval, phase_ns;
+  DevBuf<unsigned long long> rows_eval, phase_ns, trace;
   DevBuf<double> dbg_lp, dbg_lw, scratch_d;
   DevBuf<int> dbg_alloc, dbg_anc, scratch_i;
   DevBuf<uint8_t> scratch_u8;
@@ -215,9 +216,10 @@ int assign_units(pmdi_ctx* c, const double* occ) {
   std::vector<U> units;
   for (int k = 0; k < K; ++k) {
     const Dataset& s = c->ds[k];
-    const double rd = s.type == T_GAUSSIAN ? 16.0 : (s.type == T_NEGBINOM ? 8.0 : 4.0);
-    const double wr = s.type == T_GAUSSIAN ? 56.0 : (s.type == T_NEGBINOM ? 16.0 : 8.0);
-    const double cost = s.Dp * (rd * occ[k] + wr) + 2048.0;
+    // the sweep is latency-bound per 256-feature block: weight blocks by type, the fused add extra
+    const double wb = s.type == T_GAUSSIAN ? 1.0 : (s.type == T_NEGBINOM ? 0.6 : 0.5);
+    const double wf = s.type == T_GAUSSIAN ? 2.0 : 0.6;
+    const double cost = s.J * (wb * occ[k] + wf) + 0.5;
     for (int p = 0; p < P; ++p) units.push_back({cost, k, p});
   }
   std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
@@ -247,8 +249,8 @@ int assign_units(pmdi_ctx* c, const double* occ) {
   const long long fixed = 3LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 +
                           (long long)c->max_units * N * 4 + (6LL * c->max_units + 1) * 4 + 64;
   const long long avail = (long long)dev_smem - 4096 - fixed;
-  const long long want_items = (long long)c->max_units * N * c->Jmax;
-  if (avail < 12LL * c->max_units * c->Jmax * 2)
+  const long long want_items = (long long)c->max_units * N * ((c->Jmax + 3) / 4);
+  if (avail < 12LL * c->max_units * ((c->Jmax + 3) / 4) * 2)
     return fail(4, "pmdi: datasets too wide / too many particles per SM for the shared-memory work queue");
   long long items_b = std::min(want_items * 12, avail / 2);
   const long long lf_b = std::min<long long>((long long)c->lf_want * 8, avail - items_b);
@@ -585,6 +587,14 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
     sp.dbg_lp = c->dbg_lp.p; sp.dbg_lw = c->dbg_lw.p; sp.dbg_alloc = c->dbg_alloc.p; sp.dbg_anc = c->dbg_anc.p;
   }
   CK(cudaMemsetAsync(c->phase_ns.p, 0, 64 * (size_t)c->G, st));
+  sp.trace = nullptr;
+  if (getenv("PMDI_TRACE_STEP")) {
+    CK(c->trace.ensure(16 * 128));
+    CK(cudaMemsetAsync(c->trace.p, 0, 16 * 128 * 8, st));
+    sp.trace = c->trace.p;
+    sp.trace_step = atoi(getenv("PMDI_TRACE_STEP"));
+    sp.trace_cta = getenv("PMDI_TRACE_CTA") ? atoi(getenv("PMDI_TRACE_CTA")) : 0;
+  }
   c->sweep_flags = a->flags;
   c->uploaded = true;
   c->ran = false;
@@ -653,6 +663,17 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
     if (o->dbg_anc) CK(cudaMemcpyAsync(o->dbg_anc, c->dbg_anc.p, sizeof(int) * (size_t)steps * P, cudaMemcpyDeviceToHost, st));
   }
   CK(cudaStreamSynchronize(st));
+  if (c->sp.trace && getenv("PMDI_TRACE_FILE")) {
+    std::vector<unsigned long long> tr(16 * 128);
+    CK(cudaMemcpy(tr.data(), c->trace.p, tr.size() * 8, cudaMemcpyDeviceToHost));
+    FILE* f = fopen(getenv("PMDI_TRACE_FILE"), "w");
+    if (f) {
+      for (int w = 0; w < 16; ++w)
+        for (unsigned long long i = 1; i <= tr[w * 128] && i < 128; ++i)
+          fprintf(f, "%d %llu %llu\n", w, tr[w * 128 + i] >> 48, tr[w * 128 + i] & 0xFFFFFFFFFFFFull);
+      fclose(f);
+    }
+  }
   if (err != 0)
     return fail(50 + err, err == 77 ? "pmdi_sweep: grid barrier watchdog fired (a CTA did not arrive)"
                                     : "pmdi_sweep: device-side error " + std::to_string(err));

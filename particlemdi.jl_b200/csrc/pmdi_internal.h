@@ -81,6 +81,9 @@ struct SweepParams {
   unsigned long long* rows_eval; /* [K] rows evaluated                        */
   long long* counters;    /* [0] events, [1] copies                           */
   unsigned long long* phase_ns;  /* [G][8] per-CTA per-phase time (optional)  */
+  /* per-warp event trace of one CTA and one step (optional): [NW][128] (tag << 48 | clock) */
+  unsigned long long* trace;
+  int trace_cta, trace_step;
   /* debug capture */
   double* dbg_lp;
   double* dbg_lw;

@@ -84,7 +84,7 @@ __device__ int block_excl_scan(const int* in, int* out, int P, int* s_tmp /* PMD
 // The Fisher-Yates shuffle followed by partstar[1]=1 and sort! only decides WHICH element of the
 // sorted systematic sample is replaced by the reference particle: the one the shuffle moves to
 // position 1.  That index is traced through the swaps without moving anything.
-__device__ void resample_plan(const SweepParams& sp, int step, int ev, double mx, const double* lw,
+__device__ __noinline__ void resample_plan(const SweepParams& sp, int step, int ev, double mx, const double* lw,
                               int* s_tmp) {
   const int P = sp.P, t = threadIdx.x;
   const int* slot_cur = sp.slot_of + (ev & 1) * P;
@@ -187,6 +187,26 @@ struct CtaTables {
   double* lp_s;     // [NW][Npad]       per-warp proposal scratch
 };
 
+// cluster_add! of the pending row of every unit against observation buffer xb (resampling steps:
+// the copies need the statistics up to date).
+__device__ __noinline__ void flush_adds(const SweepParams& sp, const CtaTables& T, int nu, const unsigned char* xb,
+                                        const double* lf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = PMDI_NT / 32, N = sp.N;
+  for (int it = warp; it < nu * sp.Jmax; it += NW) {
+    const int u = it / sp.Jmax, j = it - u * sp.Jmax;
+    const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
+    const DsDev& ds = sp.ds[k];
+    if (j >= ds.J || T.pend[u] < 0) continue;
+    const int label = T.pend[u] & 0xFF, n = T.pend[u] >> 8;
+    const long long row = (long long)slot * N + label;
+    if (ds.type == T_GAUSSIAN) gauss_add_block(ds, row, j, n, (const double*)(xb + ds.x_off), lane);
+    else if (ds.type == T_CATEGORICAL) cat_add_block(ds, row, j, (const int*)(xb + ds.x_off), lane);
+    else nb_add_block(ds, row, j, n, (const int*)(xb + ds.x_off), lane, lf, sp.lf_T);
+  }
+  __syncthreads();
+  for (int u = threadIdx.x; u < nu; u += PMDI_NT) T.pend[u] = -1;
+}
+
 // Proposal for one unit (dataset k, particle slot), by one warp: src/pmdi.jl:223-265.
 __device__ __noinline__ void propose_unit(const SweepParams& sp, const CtaTables& T, int u, int step, int ev,
                                           unsigned* rows_eval_s) {
@@ -206,7 +226,8 @@ __device__ __noinline__ void propose_unit(const SweepParams& sp, const CtaTables
   for (int e = lane; e < cnt; e += 32) {
     const unsigned ent = T.urow[(size_t)u * N + e];
     double a = ds.rc[ent >> 8];
-    for (int j = 0; j < ds.J; ++j) a += part[e * ds.J + j];
+    const int JQ = (ds.J + PMDI_QB - 1) / PMDI_QB;
+    for (int q = 0; q < JQ; ++q) a += part[e * JQ + q];
     lps[ent & 0xFF] = a;
   }
   __syncwarp();
@@ -339,6 +360,12 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
     sm.t_prev = now_;                                    \
   }
 
+  int tr_n = 0;
+#define TRACE(tag_)                                                                              \
+  if (sp.trace && cta == sp.trace_cta && step == sp.trace_step && lane == 0 && tr_n < 127) {     \
+    sp.trace[warp * 128 + (++tr_n)] = ((unsigned long long)(tag_) << 48) | (clock64() & 0xFFFFFFFFFFFFull); \
+    sp.trace[warp * 128] = tr_n;                                                                 \
+  }
   // occupied rows of every owned unit, from the statistics in HBM
   auto rebuild_rows = [&]() {
     for (int u = warp; u < nu; u += NW) {
@@ -366,23 +393,6 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
       for (int o = tid * 16; o < bytes; o += PMDI_NT * 16) cp_async16(dst + o, src + o);
     }
   };
-  // cluster_add! of the pending row of every unit, against observation buffer xb (resampling steps)
-  auto flush_adds = [&](const unsigned char* xb) {
-    for (int it = warp; it < nu * sp.Jmax; it += NW) {
-      const int u = it / sp.Jmax, j = it - u * sp.Jmax;
-      const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
-      const DsDev& ds = sp.ds[k];
-      if (j >= ds.J || T.pend[u] < 0) continue;
-      const int label = T.pend[u] & 0xFF, n = T.pend[u] >> 8;
-      const long long row = (long long)slot * N + label;
-      if (ds.type == T_GAUSSIAN) gauss_add_block(ds, row, j, n, (const double*)(xb + ds.x_off), lane);
-      else if (ds.type == T_CATEGORICAL) cat_add_block(ds, row, j, (const int*)(xb + ds.x_off), lane);
-      else nb_add_block(ds, row, j, n, (const int*)(xb + ds.x_off), lane, lf, lfT);
-    }
-    __syncthreads();
-    for (int u = tid; u < nu; u += PMDI_NT) T.pend[u] = -1;
-  };
-
   __syncthreads();  // uinfo is visible to every warp
   rebuild_rows();
   prefetch_obs(0, 0);
@@ -395,6 +405,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
     const uint8_t* lab_g = sp.lab + (size_t)par * K * P;
     const double* inc_g = sp.inc + (size_t)par * K * P;
 
+    TRACE(1)
     cp_async_commit_wait_all();   // this step's observation has landed (own copies)
     __syncthreads();              // ... everybody's; last step's row lists are complete
     prefetch_obs(step + 1, (step + 1) % 3);
@@ -403,7 +414,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
       for (int ub = 0; ub < nu; ub += 32) {
         const int u = ub + lane;
         int c = 0;
-        if (u < nu) c = T.ucount[u] * sp.ds[T.uinfo[u] >> 24].J;
+        if (u < nu) c = T.ucount[u] * ((sp.ds[T.uinfo[u] >> 24].J + PMDI_QB - 1) / PMDI_QB);
         int inc = c;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -429,13 +440,14 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
         const int mid = (lo + hi + 1) >> 1;
         if (T.uoff[mid] <= it) lo = mid; else hi = mid - 1;
       }
-      const int J = sp.ds[T.uinfo[lo] >> 24].J;
+      const int JQ = (sp.ds[T.uinfo[lo] >> 24].J + PMDI_QB - 1) / PMDI_QB;
       const int r = it - T.uoff[lo];
-      const int e = r / J;
-      T.items[it] = ((unsigned)lo << 13) | ((unsigned)e << 5) | (unsigned)(r - e * J);
+      const int e = r / JQ;
+      T.items[it] = ((unsigned)lo << 13) | ((unsigned)e << 5) | (unsigned)(r - e * JQ);
     }
     __syncthreads();
     PHASE_MARK(0)
+    TRACE(2)
     // ------------------------------------------------------------------ the item queue
     for (;;) {
       int it = 0;
@@ -443,26 +455,40 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
       it = __shfl_sync(FULL, it, 0);
       if (it >= total) break;
       const unsigned code = T.items[it];
-      const int u = code >> 13, e = (code >> 5) & 0xFF, j = code & 31;
+      TRACE(0x100 | (code & 0xFF) | ((T.uinfo[code >> 13] >> 24) << 12))
+      const int u = code >> 13, e = (code >> 5) & 0xFF, qd = code & 31;
       const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
       const DsDev& ds = sp.ds[k];
       const unsigned ent = T.urow[(size_t)u * N + e];
       const int m = ent & 0xFF, n = ent >> 8;
       const long long row = (long long)slot * N + m;
+      const int j0 = qd * PMDI_QB, j1 = min(ds.J, j0 + PMDI_QB);
       const int pd = T.pend[u];
       const bool fused = (pd >= 0) && ((pd & 0xFF) == m);  // pending add of the previous step (n == pd >> 8)
       double v;
       if (ds.type == T_GAUSSIAN) {
-        if (fused) v = gauss_fused_block(ds, row, j, n, (const double*)(xs_prev + ds.x_off),
-                                         (const double*)(xs_cur + ds.x_off), lane);
-        else v = gauss_eval_block(ds, row, j, n, (const double*)(xs_cur + ds.x_off), lane);
+        if (fused) {
+          v = 0.0;
+          for (int j = j0; j < j1; ++j)
+            v += gauss_fused_block(ds, row, j, n, (const double*)(xs_prev + ds.x_off),
+                                   (const double*)(xs_cur + ds.x_off), lane);
+        } else {
+          v = gauss_eval_item(ds, row, j0, j1, n, (const double*)(xs_cur + ds.x_off), lane);
+        }
       } else if (ds.type == T_CATEGORICAL) {
-        if (fused) { cat_add_block(ds, row, j, (const int*)(xs_prev + ds.x_off), lane); __syncwarp(); }
-        v = cat_eval_block(ds, row, j, (const int*)(xs_cur + ds.x_off), lane);
+        if (fused) {
+          for (int j = j0; j < j1; ++j) cat_add_block(ds, row, j, (const int*)(xs_prev + ds.x_off), lane);
+          __syncwarp();
+        }
+        v = cat_eval_item(ds, row, j0, j1, (const int*)(xs_cur + ds.x_off), lane);
       } else {
-        if (fused) { nb_add_block(ds, row, j, n, (const int*)(xs_prev + ds.x_off), lane, lf, lfT); __syncwarp(); }
-        v = nb_eval_block(ds, row, j, n, (const int*)(xs_cur + ds.x_off), lane, lf, lfT);
+        if (fused) {
+          for (int j = j0; j < j1; ++j) nb_add_block(ds, row, j, n, (const int*)(xs_prev + ds.x_off), lane, lf, lfT);
+          __syncwarp();
+        }
+        v = nb_eval_item(ds, row, j0, j1, n, (const int*)(xs_cur + ds.x_off), lane, lf, lfT);
       }
+      TRACE(3)
       int last = 0;
       if (lane == 0) {
         T.part[it] = v;
@@ -472,14 +498,18 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
       last = __shfl_sync(FULL, last, 0);
       if (last) {  // this warp finished the unit: run its proposal now
         __threadfence_block();
+        TRACE(4)
         propose_unit(sp, T, u, step, ev, sm.rows_eval);
+        TRACE(5)
       }
     }
+    TRACE(6)
     for (int u = warp; u < nu; u += NW)  // units with no occupied row at all
       if (T.uoff[u + 1] == T.uoff[u]) propose_unit(sp, T, u, step, ev, sm.rows_eval);
     PHASE_MARK(1)
     if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
     PHASE_MARK(4)
+    TRACE(7)
 
     // ------------------------------------------------------------------ weights + ESS
     double mx = -INFINITY;
@@ -517,9 +547,10 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
     const bool do_res = (num * num) / den <= 0.5 * (double)P;  // src/pmdi.jl:317
     if (!do_res && cta == 0 && tid == 0) sp.ev_of_step[step] = -1;
     PHASE_MARK(5)
+    TRACE(8)
 
     if (do_res) {
-      flush_adds(xs_cur);
+      flush_adds(sp, T, nu, xs_cur, lf);
       if (cta == 0) resample_plan(sp, step, ev, mx, lw, s_tmp);
       if (!grid_barrier(sp.bar, epoch, G, sp.err)) return;
       const int ncopy = ldcg_i32(sp.plan_out);
