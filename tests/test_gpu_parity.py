@@ -80,3 +80,79 @@ def test_sweep_with_feature_flags():
     flags = [(rng.random(d.shape[1]) < 0.6).astype(np.uint8) for d in pr["data"]]
     ref, got = _run_both(pr, flags=flags)
     _assert_parity(pr, ref, got)
+
+
+def test_sstar_compat_flag():
+    """pmdi()'s own (unpermuted) trajectory emission, src/pmdi.jl:321-324."""
+    from oracle import oracle as orc
+    import pmdi_b200.capi as capi
+    pr = problem(**CASES["mixed_k3"], seed=9)
+    o = orc.Oracle(pr["data"], pr["types"], pr["N"], pr["P"])
+    ref = o.sweep(pr["s"], pr["order"], pr["n1"], pr["Pi"], pr["phi"],
+                  mode=orc.MODE_DENSE | orc.MODE_SSTAR_COMPAT, seed=2, it=1)
+    with capi.Context(pr["data"], pr["types"], pr["N"], pr["P"]) as ctx:
+        got = ctx.sweep(pr["s"], pr["order"], pr["n1"], pr["Pi"], pr["phi"], seed=2, it=1, sstar_compat=True)
+    assert ref["n_resamples"] > 0
+    np.testing.assert_array_equal(got["s"], ref["s"])
+    assert got["p_star"] == ref["p_star"]
+
+
+EDGE = {
+    "smallest_N_P_empty_prefix": dict(sets=[(G, 3, 0), (C, 2, 2)], n=12, N=2, P=2, rho=0.1),
+    "one_step": dict(sets=[(NB, 5, 0)], n=10, N=3, P=4, rho=0.999),
+    "ragged_widths": dict(sets=[(G, 1, 0), (G, 257, 0), (C, 63, 5), (NB, 65, 0)], n=40, N=4, P=9),
+    "N_equals_n": dict(sets=[(G, 6, 0)], n=16, N=16, P=12),
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE))
+def test_edge_cases(name):
+    pr = problem(**EDGE[name], seed=10)
+    ref, got = _run_both(pr, lw0=1.0)
+    _assert_parity(pr, ref, got)
+
+
+@pytest.mark.parametrize("name", __import__("helpers").GOLDEN)
+def test_cuda_matches_golden_fixture(name):
+    """Committed fixtures (tests/golden/make_golden.py): no oracle at run time."""
+    from helpers import assert_matches_golden, load_golden
+    import pmdi_b200.capi as capi
+    pr, tapes, z = load_golden(name)
+    with capi.Context(pr["data"], pr["types"], pr["N"], pr["P"]) as ctx:
+        got = ctx.sweep(pr["s"], pr["order"], pr["n1"], pr["Pi"], pr["phi"], seed=int(z["seed"]),
+                        it=int(z["it"]), tapes=tapes, debug=True, logweight_init=float(z["lw0"]))
+    assert_matches_golden(got, z, rtol=RTOL)
+
+
+def test_chained_sweeps_match_oracle():
+    """Three MCMC iterations through one context (state is rebuilt per sweep, src/pmdi.jl:165-172)."""
+    from oracle import oracle as orc
+    import pmdi_b200.capi as capi
+    pr = problem(**CASES["mixed_k3"], seed=11)
+    o = orc.Oracle(pr["data"], pr["types"], pr["N"], pr["P"])
+    rng = np.random.default_rng(3)
+    s_ref = s_got = pr["s"]
+    with capi.Context(pr["data"], pr["types"], pr["N"], pr["P"]) as ctx:
+        for it in range(3):
+            order = rng.permutation(pr["n"]) + 1
+            ref = o.sweep(s_ref, order, pr["n1"], pr["Pi"], pr["phi"], seed=8, it=it, logweight_init=float(it > 0))
+            got = ctx.sweep(s_got, order, pr["n1"], pr["Pi"], pr["phi"], seed=8, it=it, logweight_init=float(it > 0))
+            np.testing.assert_array_equal(got["s"], ref["s"])
+            assert got["p_star"] == ref["p_star"]
+            s_ref, s_got = ref["s"], got["s"]
+
+
+def test_argument_errors_are_reported():
+    import pmdi_b200.capi as capi
+    pr = problem(**CASES["gauss_small"], seed=3)
+    with capi.Context(pr["data"], pr["types"], pr["N"], pr["P"]) as ctx:
+        bad = pr["order"].copy()
+        bad[0] = bad[1]
+        with pytest.raises(capi.PmdiError, match="permutation"):
+            ctx.sweep(pr["s"], bad, pr["n1"], pr["Pi"], pr["phi"])
+        s_bad = pr["s"].copy()
+        s_bad[0, 0] = pr["N"] + 1
+        with pytest.raises(capi.PmdiError, match="label"):
+            ctx.sweep(s_bad, pr["order"], pr["n1"], pr["Pi"], pr["phi"])
+        with pytest.raises(capi.PmdiError, match="n1"):
+            ctx.sweep(pr["s"], pr["order"], 0, pr["Pi"], pr["phi"])
