@@ -32,7 +32,7 @@ __global__ void k_sweep_init(SweepParams sp) {
     sp.logical_of[sp.P + t] = t;
   }
   if (t == 0) {
-    *sp.bar = 0u;
+    *(unsigned long long*)sp.bar = 0ull;
     *sp.err = 0;
     sp.counters[0] = sp.counters[1] = sp.counters[2] = 0;
     sp.plan_out[0] = 0;
@@ -131,7 +131,7 @@ __global__ void k_proto_aux(SweepParams sp) {
   const int n = ds.n[row];
   for (int j = w; j < ds.J; j += blockDim.x >> 5) {
     if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);
-    else if (ds.type == T_NEGBINOM) nb_aux_block(ds, row, j, n, lane, sp.lf_glob, sp.lf_T);
+    else if (ds.type == T_NEGBINOM) nb_aux_block(ds, row, j, n, lane, sp.lf_glob, sp.lf_glob_T);
     else if (lane == 0) ds.aux[row * ds.J + j] = 0.0;
   }
 }
@@ -287,7 +287,7 @@ __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
     double v;
     if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, n, (const double*)xs_raw, lane);
     else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)xs_raw, lane);
-    else v = nb_eval_block(ds, row, j, n, (const int*)xs_raw, lane, sp.lf_glob, sp.lf_T);
+    else v = nb_eval_block(ds, row, j, n, (const int*)xs_raw, lane, sp.lf_glob, sp.lf_glob_T);
     acc += v;
   }
   if (lane == 0) *out = acc;
@@ -309,7 +309,7 @@ __global__ void k_aux_one(SweepParams sp, int k) {
   const int n = ds.n[row];
   for (int j = w; j < ds.J; j += blockDim.x >> 5) {
     if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);
-    else if (ds.type == T_NEGBINOM) nb_aux_block(ds, row, j, n, lane, sp.lf_glob, sp.lf_T);
+    else if (ds.type == T_NEGBINOM) nb_aux_block(ds, row, j, n, lane, sp.lf_glob, sp.lf_glob_T);
     else if (lane == 0) ds.aux[row * ds.J + j] = 0.0;
   }
 }
@@ -339,7 +339,7 @@ __global__ void k_empty_lp(SweepParams sp, double* lp_empty) {
     double v;
     if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, 0, (const double*)(xs_raw + ds.x_off), lane);
     else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)(xs_raw + ds.x_off), lane);
-    else v = nb_eval_block(ds, row, j, 0, (const int*)(xs_raw + ds.x_off), lane, sp.lf_glob, sp.lf_T);
+    else v = nb_eval_block(ds, row, j, 0, (const int*)(xs_raw + ds.x_off), lane, sp.lf_glob, sp.lf_glob_T);
     if (lane == 0) part[k][j] = v;
   }
   __syncthreads();

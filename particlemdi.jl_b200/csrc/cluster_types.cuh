@@ -11,7 +11,7 @@
 #pragma once
 #include "device_utils.cuh"
 
-#define PMDI_QB 4 /* 256-feature blocks per work item */
+
 
 // ------------------------------------------------------------------------------------------
 // Gaussian — reference src/datatypes/gaussian_cluster.jl:37-52 (calc_logprob), :54-66 (cluster_add!)
@@ -61,7 +61,7 @@ __device__ __forceinline__ double div_const(double x, double c, double rc) {
 // rounded, no FMA contraction across the reference's operations), so the stored statistics follow
 // the reference's to the bit; n is the size AFTER the add.  The new aux (sum of 0.5 log lamn over
 // the flagged features) is taken as one log of the lane's product of <= 8 factors.
-__device__ __forceinline__ void gauss_add_block(const DsDev& ds, long long row, int j, int n,
+__device__ __noinline__ void gauss_add_block(const DsDev& ds, long long row, int j, int n,
                                                 const double* xs, int lane) {
   const int q0 = j * PMDI_FB;
   const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
@@ -111,7 +111,7 @@ __device__ __forceinline__ void gauss_add_block(const DsDev& ds, long long row, 
       *(double2*)(ds.mu + o) = mu[it];
       *(double2*)(ds.lamn + o) = ln[it];
     }
-  const double acc = warp_sum(0.5 * log(prod));
+  const double acc = warp_sum(0.5 * pm_log(prod));
   if (lane == 0) ds.aux[row * ds.J + j] = acc;
 }
 
@@ -174,7 +174,7 @@ __device__ __noinline__ double gauss_fused_raw(double* sum_p, double* beta_p, do
         *(double2*)(lamn_p + o) = ln[i];
       }
   }
-  double a = 0.5 * log(prodl), e = log(prode);
+  double a = 0.5 * pm_log(prodl), e = pm_log(prode);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     a += __shfl_xor_sync(FULL, a, o);
@@ -238,7 +238,7 @@ __device__ __forceinline__ double cat_eval_block(const DsDev& ds, long long row,
   return warp_sum(log(prod));
 }
 
-__device__ __forceinline__ void cat_add_block(const DsDev& ds, long long row, int j, const int* xs,
+__device__ __noinline__ void cat_add_block(const DsDev& ds, long long row, int j, const int* xs,
                                               int lane) {
   const int q0 = j * PMDI_FB;
   const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
@@ -279,7 +279,7 @@ __device__ __forceinline__ double nb_eval_block(const DsDev& ds, long long row, 
 }
 
 // n is the size AFTER the add
-__device__ __forceinline__ void nb_add_block(const DsDev& ds, long long row, int j, int n,
+__device__ __noinline__ void nb_add_block(const DsDev& ds, long long row, int j, int n,
                                              const int* xs, int lane, const double* lf, int T) {
   const int q0 = j * PMDI_FB;
   const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
@@ -370,7 +370,7 @@ __device__ __noinline__ double gauss_eval_raw(const double* mu, const double* lm
     PMDI_G_STEP(m1, l1, 1)
     PMDI_G_STEP(m2, l2, 2)
     PMDI_G_STEP(m3, l3, 3)
-    acc += log(prod);
+    acc += pm_log(prod);
     mu += PMDI_FB; lm += PMDI_FB; xs += PMDI_FB * 8;
     if (flag) flag += PMDI_FB;
   }
@@ -394,10 +394,7 @@ __device__ __forceinline__ double gauss_eval_item(const DsDev& ds, long long row
 // log-factorial with the table in shared memory (address lf_s), Stirling beyond T
 __device__ __forceinline__ double lfact_s(long long k, unsigned lf_s, int T) {
   if (k < (long long)T) return lds_f64(lf_s + (unsigned)k * 8u);
-  const double z = (double)k + 1.0;
-  const double zi = 1.0 / z, zi2 = zi * zi;
-  return (z - 0.5) * log(z) - z + 0.91893853320467274178 +
-         zi * (1.0 / 12.0 - zi2 * (1.0 / 360.0 - zi2 * (1.0 / 1260.0)));
+  return pm_lfact_stirling(k);
 }
 
 __device__ __noinline__ double nb_eval_raw(const long long* S, const double* aux, unsigned xs, int nits,
@@ -470,7 +467,7 @@ __device__ __noinline__ double cat_eval_raw(const uint32_t* cnt, long long Dp, u
     PMDI_C_STEP(v1, a1, b1, 1)
     PMDI_C_STEP(v2, a2, b2, 2)
     PMDI_C_STEP(v3, a3, b3, 3)
-    acc += log(prod);
+    acc += pm_log(prod);
     cnt += PMDI_FB; xs += PMDI_FB * 4;
   }
 #undef PMDI_C_STEP
@@ -489,7 +486,7 @@ __device__ __forceinline__ double cat_eval_item(const DsDev& ds, long long row, 
 // Row movement for resampling (src/pmdi.jl:318-341 in dense form): one warp moves one cluster
 // row src -> dst, or resets dst to the empty state when the source label is empty.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void row_copy(const DsDev& ds, long long src, long long dst, int lane) {
+__device__ __noinline__ void row_copy(const DsDev& ds, long long src, long long dst, int lane) {
   const int ns = ldcg_i32(ds.n + src), nd = ldcg_i32(ds.n + dst);
   if (ns == 0 && nd == 0) return;
   const int Dp = ds.Dp;

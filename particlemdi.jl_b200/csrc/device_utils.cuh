@@ -30,6 +30,23 @@ __host__ __device__ __forceinline__ double pmdi_philox_uniform(unsigned long lon
   return (double)(x >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// One copy each of the long FP64 routines inside the persistent kernel: the sweep's per-step
+// code has to stay resident in the instruction cache (the math library inlines ~2-4 KB per call
+// site).  Same routines, same bits as the inlined forms.
+__device__ __noinline__ double pm_log(double x) { return log(x); }
+__device__ __noinline__ double pm_exp(double x) { return exp(x); }
+__device__ __noinline__ double pm_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __noinline__ double pm_uniform(unsigned long long seed, unsigned iter, unsigned kind, unsigned step,
+                                          unsigned k, unsigned index) {
+  return pmdi_philox_uniform(seed, iter, kind, step, k, index);
+}
+__device__ __noinline__ double pm_lfact_stirling(long long k) {
+  const double z = (double)k + 1.0;
+  const double zi = 1.0 / z, zi2 = zi * zi;
+  return (z - 0.5) * log(z) - z + 0.91893853320467274178 +
+         zi * (1.0 / 12.0 - zi2 * (1.0 / 360.0 - zi2 * (1.0 / 1260.0)));
+}
+
 // Butterfly reductions: every lane ends with the same bits (a+b == b+a, identical tree shape).
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -54,10 +71,7 @@ __device__ __forceinline__ uint8_t ldcg_u8(const uint8_t* p) { return __ldcg(p);
 // (z >= 256: the first omitted term 1/(1680 z^7) is < 1e-20).
 __device__ __forceinline__ double lfact(long long k, const double* tab, int T) {
   if (k < (long long)T) return tab[k];
-  const double z = (double)k + 1.0;
-  const double zi = 1.0 / z, zi2 = zi * zi;
-  return (z - 0.5) * log(z) - z + 0.91893853320467274178 +
-         zi * (1.0 / 12.0 - zi2 * (1.0 / 360.0 - zi2 * (1.0 / 1260.0)));
+  return pm_lfact_stirling(k);
 }
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {

@@ -246,11 +246,11 @@ int assign_units(pmdi_ctx* c, const double* occ) {
   const int Npad = (N + 31) & ~31;
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  const long long fixed = 3LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 +
-                          (long long)c->max_units * N * 4 + (6LL * c->max_units + 1) * 4 + 64;
+  const long long fixed = 3LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 +
+                          (long long)c->max_units * N * 4 + (10LL * c->max_units + 2) * 4 + 64;
   const long long avail = (long long)dev_smem - 4096 - fixed;
-  const long long want_items = (long long)c->max_units * N * ((c->Jmax + 3) / 4);
-  if (avail < 12LL * c->max_units * ((c->Jmax + 3) / 4) * 2)
+  const long long want_items = (long long)c->max_units * N * c->Jmax;
+  if (avail < 12LL * c->max_units * c->Jmax * 2)
     return fail(4, "pmdi: datasets too wide / too many particles per SM for the shared-memory work queue");
   long long items_b = std::min(want_items * 12, avail / 2);
   const long long lf_b = std::min<long long>((long long)c->lf_want * 8, avail - items_b);
@@ -282,7 +282,8 @@ int fill_params(pmdi_ctx* c) {
   sp.Jmax = c->Jmax;
   sp.cta_off = c->d_cta_off.p; sp.cta_units = c->d_cta_units.p;
   sp.max_units = c->max_units; sp.sm_x_bytes = c->sm_x_bytes; sp.lf_T = c->lf_T;
-  sp.item_cap = c->item_cap; sp.lf_glob = c->lf_dev.p;
+  sp.item_cap = c->item_cap; sp.lf_glob = c->lf_dev.p; sp.lf_glob_T = c->lf_want;
+  sp.qb = getenv("PMDI_QB") ? std::max(1, atoi(getenv("PMDI_QB"))) : 2;
   return 0;
 }
 

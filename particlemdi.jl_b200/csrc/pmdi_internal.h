@@ -59,8 +59,8 @@ struct SweepParams {
   double* lw_out;         /* [P] final log-weights (written by CTA 0)        */
   int* slot_of;           /* [2][P] logical -> slot, double-buffered by resampling event */
   int* logical_of;        /* [2][P] slot -> logical                          */
-  uint8_t* lab;           /* [2][K][P] by slot: label chosen this step (0-based), double-buffered by step */
-  double* inc;            /* [2][K][P] by slot: incremental log-weight of this step              */
+  uint8_t* lab;           /* [2][K][P] by logical particle: label chosen this step (0-based), double-buffered by step */
+  double* inc;            /* [2][K][P] by logical particle: incremental log-weight of this step  */
   const double* lp_empty; /* [steps][K] predictive of the empty cluster for every swept observation */
   uint8_t* alloc_log;     /* [steps][K][P] by logical particle               */
   int* anc_log;           /* [events][P] 1-based ancestors                   */
@@ -75,8 +75,10 @@ struct SweepParams {
   const int* cta_units;   /* k << 24 | slot                                   */
   int max_units, sm_x_bytes;
   int lf_T, item_cap;   /* log-factorial entries in smem; capacity of the per-step item queue */
-  const double* lf_glob;  /* log-factorial table [lf_T]                       */
-  unsigned* bar;          /* grid barrier counter                             */
+  int qb;               /* 256-feature blocks per plain work item            */
+  const double* lf_glob;  /* log-factorial table in HBM [lf_glob_T]; its first lf_T entries are staged in smem */
+  int lf_glob_T;
+  unsigned* bar;          /* grid barrier arrival counter (64-bit, 16 bytes reserved) */
   int* err;
   unsigned long long* rows_eval; /* [K] rows evaluated                        */
   long long* counters;    /* [0] events, [1] copies                           */
