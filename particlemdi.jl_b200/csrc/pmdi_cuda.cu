@@ -90,7 +90,6 @@ struct pmdi_ctx {
   std::vector<int> cta_off, cta_units;
   int max_units = 0, sm_x_bytes = 0, lf_T = 0, lf_want = 0, item_cap = 0, Jmax = 0;
   bool assigned = false;
-  std::vector<double> last_occ;
   size_t dyn_smem = 0;
   std::vector<double> lf_host;
   DevBuf<double> lf_dev;
@@ -100,14 +99,14 @@ struct pmdi_ctx {
   DevBuf<long long> s_in, s_out, d_pstar, cluster_n, counters;
   DevBuf<int> order, slot_of, anc_log, ev_of_step, members, mem_off, cur_at, plan_out, err;
   DevBuf<int> sc_j, sc_anc0, sc_a, sc_b, sc_c, sc_d;
-  DevBuf<double> lw, lw_out, sc_w, sc_pp, sc_u, inc, lp_empty;
+  DevBuf<double> lw, lw_out, sc_w, sc_pp, sc_u, inc, lp_empty, ess_part;
   DevBuf<int> logical_of;
   DevBuf<uint8_t> lab, alloc_log;
   DevBuf<int2> copies;
   DevBuf<unsigned> bar;
   DevBuf<unsigned long long> rows_eval, phase_ns, trace;
   DevBuf<double> dbg_lp, dbg_lw, scratch_d;
-  DevBuf<int> dbg_alloc, dbg_anc, scratch_i;
+  DevBuf<int> dbg_alloc, dbg_anc, scratch_i, wd_state;
   DevBuf<uint8_t> scratch_u8;
   SweepParams sp;
   bool uploaded = false, ran = false;
@@ -206,59 +205,44 @@ int build_layout(pmdi_ctx* c) {
   return 0;
 }
 
-// Units (dataset, particle slot) -> CTAs: longest-processing-time greedy on the bytes a unit streams
-// per observation step (occupied rows read + one row read-modify-written), so that every CTA moves a
-// similar number of bytes.  occ[k] = occupied labels expected for dataset k (from the prefix).
-// Then the shared-memory budget of the sweep kernel.
-int assign_units(pmdi_ctx* c, const double* occ) {
-  const int K = c->K, P = c->P, N = c->N, G = c->G;
-  struct U { double cost; int k, slot; };
-  std::vector<U> units;
-  for (int k = 0; k < K; ++k) {
-    const Dataset& s = c->ds[k];
-    // the sweep is latency-bound per 256-feature block: weight blocks by type, the fused add extra
-    const double wb = s.type == T_GAUSSIAN ? 1.0 : (s.type == T_NEGBINOM ? 0.6 : 0.5);
-    const double wf = s.type == T_GAUSSIAN ? 2.0 : 0.6;
-    const double cost = s.J * (wb * occ[k] + wf) + 0.5;
-    for (int p = 0; p < P; ++p) units.push_back({cost, k, p});
-  }
-  std::stable_sort(units.begin(), units.end(), [](const U& a, const U& b) { return a.cost > b.cost; });
-  typedef std::pair<double, int> QE;
-  std::priority_queue<QE, std::vector<QE>, std::greater<QE>> pq;
-  for (int g = 0; g < G; ++g) pq.push({0.0, g});
-  std::vector<std::vector<int>> per(G);
-  for (const U& u : units) {
-    QE top = pq.top();
-    pq.pop();
-    per[top.second].push_back((u.k << 24) | u.slot);
-    pq.push({top.first + u.cost, top.second});
-  }
+// Particle slots -> CTAs (all K datasets of a slot stay together: the particle's weight update is
+// CTA-local), round-robin so that the counts differ by at most one; then the shared-memory
+// budget of the sweep kernel.
+int assign_units(pmdi_ctx* c) {
+  const int K = c->K, P = c->P, N = c->N;
+  c->G = std::min(c->n_sm, P);  // one persistent CTA per SM; never a CTA without a particle
+  const int G = c->G;
   c->cta_off.assign(G + 1, 0);
   c->cta_units.clear();
-  c->max_units = 1;
+  int max_slots = 0;
   for (int g = 0; g < G; ++g) {
     c->cta_off[g] = (int)c->cta_units.size();
-    c->cta_units.insert(c->cta_units.end(), per[g].begin(), per[g].end());
-    c->max_units = std::max(c->max_units, (int)per[g].size());
+    int ns = 0;
+    for (int slot = g; slot < P; slot += G, ++ns)
+      for (int k = 0; k < K; ++k) c->cta_units.push_back((k << 24) | slot);
+    max_slots = std::max(max_slots, ns);
   }
   c->cta_off[G] = (int)c->cta_units.size();
-  // dynamic shared memory: 3 observation buffers | lf | proposal scratch | part+items | unit tables
+  c->max_units = max_slots * K;
+  // dynamic shared memory: 4 observation buffers | lf | proposal scratch | Pi | lw | inc | part x2 |
+  // items x2 | unit tables
   const int Npad = (N + 31) & ~31;
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
-  const long long fixed = 3LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 +
-                          (long long)c->max_units * N * 4 + (10LL * c->max_units + 2) * 4 + 64;
-  const long long avail = (long long)dev_smem - 4096 - fixed;
-  const long long want_items = (long long)c->max_units * N * c->Jmax;
-  if (avail < 12LL * c->max_units * c->Jmax * 2)
+  const long long MU = c->max_units, MS = max_slots;
+  const long long fixed = 4LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 +
+                          MS * 8 + 2 * MU * 8 + MU * N * 4 + (12 * MU + 2 * MS) * 4 + 64;
+  const long long avail = (long long)dev_smem - 6144 - fixed;
+  const long long want_items = MU * N * c->Jmax;  // every label of every unit occupied
+  if (avail < 24LL * MU * c->Jmax * 2)
     return fail(4, "pmdi: datasets too wide / too many particles per SM for the shared-memory work queue");
-  long long items_b = std::min(want_items * 12, avail / 2);
+  long long items_b = std::min(want_items * 24, avail / 2);
   const long long lf_b = std::min<long long>((long long)c->lf_want * 8, avail - items_b);
-  items_b = std::min(want_items * 12, avail - lf_b);
-  c->item_cap = (int)(items_b / 12);
+  items_b = std::min(want_items * 24, avail - lf_b);
+  c->item_cap = (int)(items_b / 24);
   c->lf_T = (int)(lf_b / 8);
   if (c->lf_want > 0 && c->lf_T < 256) return fail(4, "pmdi: no shared memory left for the log-factorial table");
-  c->dyn_smem = (size_t)fixed + (size_t)c->lf_T * 8 + (size_t)c->item_cap * 12;
+  c->dyn_smem = (size_t)fixed + (size_t)c->lf_T * 8 + (size_t)c->item_cap * 24;
   CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
   CK(c->d_cta_off.ensure(c->cta_off.size()));
   CK(c->d_cta_units.ensure(c->cta_units.size()));
@@ -351,7 +335,7 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   for (auto& d : c->ds) d.release();
   DevBuf<double>* dd[] = {&c->lf_dev, &c->Pi, &c->l1phi, &c->tape_alloc, &c->tape_resamp, &c->tape_shuffle,
                           &c->tape_select, &c->lw, &c->lw_out, &c->sc_w, &c->sc_pp, &c->sc_u, &c->dbg_lp,
-                          &c->dbg_lw, &c->scratch_d, &c->inc, &c->lp_empty};
+                          &c->dbg_lw, &c->scratch_d, &c->inc, &c->lp_empty, &c->ess_part};
   for (auto* b : dd) b->release();
   DevBuf<int>* di[] = {&c->d_cta_off, &c->d_cta_units, &c->order, &c->slot_of, &c->anc_log, &c->ev_of_step,
                        &c->members, &c->mem_off, &c->cur_at, &c->plan_out, &c->err, &c->sc_j, &c->sc_anc0,
@@ -495,25 +479,10 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   if (K > 1 && !a->phi) return fail(1, "pmdi_sweep: phi is required when K > 1");
   const int steps = (int)(n - a->n1 + 1);
   SweepParams& sp = c->sp;
-  {  // occupied labels in the rho-prefix of every dataset -> byte cost of a unit -> CTA assignment
-    std::vector<double> occ(K, 1.0);
-    for (int k = 0; k < K; ++k) {
-      std::vector<uint8_t> seen_l(N + 1, 0);
-      int cnt = 0;
-      for (long long t = 0; t + 1 < a->n1; ++t) {
-        const int64_t o = a->order_obs[t];
-        if (o < 1 || o > n) break;
-        const int64_t l = a->s[(size_t)(o - 1) + (size_t)n * k];
-        if (l >= 1 && l <= N && !seen_l[l]) { seen_l[l] = 1; ++cnt; }
-      }
-      occ[k] = std::max(1, cnt) + 0.5;
-    }
-    if (!c->assigned || occ != c->last_occ) {
-      rc = assign_units(c, occ.data());
-      if (rc) return rc;
-      c->last_occ = occ;
-      fill_params(c);
-    }
+  if (!c->assigned) {
+    rc = assign_units(c);
+    if (rc) return rc;
+    fill_params(c);
   }
   // validate + convert
   std::vector<int> order(n);
@@ -558,7 +527,7 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
     sp.tape_select = c->tape_select.p;
   }
   // state buffers
-  CK(c->lw.ensure((size_t)c->G * P)); CK(c->lw_out.ensure(P)); CK(c->slot_of.ensure(2 * (size_t)P));
+  CK(c->lw.ensure(P)); CK(c->ess_part.ensure(6 * (size_t)c->G)); CK(c->lw_out.ensure(P)); CK(c->slot_of.ensure(2 * (size_t)P));
   CK(c->logical_of.ensure(2 * (size_t)P)); CK(c->inc.ensure(2 * (size_t)K * P)); CK(c->lp_empty.ensure((size_t)steps * K));
   CK(c->lab.ensure(2 * (size_t)K * P)); CK(c->alloc_log.ensure((size_t)steps * K * P));
   CK(c->anc_log.ensure((size_t)steps * P)); CK(c->ev_of_step.ensure(steps));
@@ -572,7 +541,7 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   sp.n1 = (int)a->n1; sp.steps = steps; sp.flags = (int)a->flags;
   sp.Pi = c->Pi.p; sp.l1phi = c->l1phi.p; sp.s_in = c->s_in.p; sp.order = c->order.p;
   sp.lw_init = a->logweight_init; sp.seed = a->seed; sp.iter = a->iter;
-  sp.lw = c->lw.p; sp.lw_out = c->lw_out.p; sp.slot_of = c->slot_of.p; sp.logical_of = c->logical_of.p;
+  sp.lw = c->lw.p; sp.ess_part = c->ess_part.p; sp.lw_out = c->lw_out.p; sp.slot_of = c->slot_of.p; sp.logical_of = c->logical_of.p;
   sp.inc = c->inc.p; sp.lp_empty = c->lp_empty.p; sp.lab = c->lab.p; sp.alloc_log = c->alloc_log.p;
   sp.anc_log = c->anc_log.p; sp.ev_of_step = c->ev_of_step.p;
   sp.sc_w = c->sc_w.p; sp.sc_pp = c->sc_pp.p; sp.sc_u = c->sc_u.p; sp.sc_j = c->sc_j.p;
@@ -588,6 +557,9 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
     sp.dbg_lp = c->dbg_lp.p; sp.dbg_lw = c->dbg_lw.p; sp.dbg_alloc = c->dbg_alloc.p; sp.dbg_anc = c->dbg_anc.p;
   }
   CK(cudaMemsetAsync(c->phase_ns.p, 0, 64 * (size_t)c->G, st));
+  CK(c->wd_state.ensure((size_t)c->G * 16 * 16));
+  CK(cudaMemsetAsync(c->wd_state.p, 0xff, sizeof(int) * (size_t)c->G * 16 * 16, st));
+  sp.wd_state = c->wd_state.p;
   sp.trace = nullptr;
   if (getenv("PMDI_TRACE_STEP")) {
     CK(c->trace.ensure(16 * 128));
@@ -675,8 +647,22 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
       fclose(f);
     }
   }
+  if (err == 79 && getenv("PMDI_WD_DUMP")) {
+    std::vector<int> w((size_t)c->G * 16 * 16);
+    CK(cudaMemcpy(w.data(), c->wd_state.p, w.size() * 4, cudaMemcpyDeviceToHost));
+    for (int g = 0; g < c->G; ++g)
+      for (int wp = 0; wp < 16; ++wp) {
+        const int* v = &w[((size_t)g * 16 + wp) * 16];
+        if (v[0] == -1 && v[11] == -1) continue;
+        fprintf(stderr, "cta %d warp %d: t=%d h=%d gen=%d head=%d tail=%d units_in=%d left=%d res_step=%d res_flag=%d "
+                        "arrived=%d claim=%d nu=%d parked=%d gen'=%d units_in'=%d pdone=%d\n", g, wp, v[0], v[1], v[2],
+                v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15]);
+      }
+  }
   if (err != 0)
     return fail(50 + err, err == 77 ? "pmdi_sweep: grid barrier watchdog fired (a CTA did not arrive)"
+                          : err == 79 ? "pmdi_sweep: work-queue watchdog fired (a warp waited 4 s for work)"
+                          : err == 78 ? "pmdi_sweep: shared-memory work queue overflow (too many occupied clusters per SM)"
                                     : "pmdi_sweep: device-side error " + std::to_string(err));
   if (o->p_star) *o->p_star = pstar;
   o->n_resamples = counters[0];

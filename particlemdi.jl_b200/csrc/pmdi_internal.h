@@ -55,7 +55,8 @@ struct SweepParams {
   int Jmax;                /* max over datasets of J                          */
   const double *tape_alloc, *tape_resamp, *tape_shuffle, *tape_select;
   /* state */
-  double* lw;             /* [G][P] per-CTA private copy of the log-weights, by logical particle */
+  double* lw;             /* [P] log-weights by logical particle (each written by the CTA that owns the particle) */
+  double* ess_part;       /* [2][G][3] per step parity and CTA: max log-weight, sum w, sum w^2 (w = exp(l - max)) */
   double* lw_out;         /* [P] final log-weights (written by CTA 0)        */
   int* slot_of;           /* [2][P] logical -> slot, double-buffered by resampling event */
   int* logical_of;        /* [2][P] slot -> logical                          */
@@ -86,6 +87,7 @@ struct SweepParams {
   /* per-warp event trace of one CTA and one step (optional): [NW][128] (tag << 48 | clock) */
   unsigned long long* trace;
   int trace_cta, trace_step;
+  int* wd_state;          /* [G][NW][16] where every warp was when a watchdog fired */
   /* debug capture */
   double* dbg_lp;
   double* dbg_lw;

@@ -1,73 +1,35 @@
-// The conditional-SMC sweep as ONE persistent cooperative kernel: the per-observation loop of
-// the reference (src/pmdi.jl:209-342) runs on the device with no host involvement.  One CTA per
-// SM.  Every (dataset, particle-slot) unit of statistics is owned by one CTA for the whole sweep,
-// so predictive, proposal and add of a unit are CTA-local; only the particle weights need the
-// whole grid, and that exchange is SPLIT-PHASE: a CTA arrives at the grid barrier of step t when
-// its proposals are out, starts the predictive pass of step t+1 at once, and only looks at the
-// other CTAs' increments (weights + ESS of step t) when the first of its units is ready to
-// propose for step t+1.  Barrier latency and step-to-step imbalance between CTAs hide behind the
-// next step's streaming; the rare resampling step (ESS <= P/2) discards that pass and redoes it
-// after the particles have moved.
+// The conditional-SMC sweep as ONE persistent kernel: the per-observation loop of the reference
+// (src/pmdi.jl:209-342) runs on the device as a DATAFLOW over (dataset, particle) units, with no
+// host involvement and no CTA-wide or grid-wide wait on the common path.
 //
-// Per observation step t a CTA runs:
-//   top       wait for the staged observation, prefetch the next one (cp.async, 3-deep ring: the
-//             previous row is still needed by the fused add), build this step's item list;
-//   queue     ONE dynamically scheduled list of work items handed to warps through a
-//             shared-memory counter, longest first:
-//               fused item  = the row the particle chose in step t-1, one 256-feature block:
-//                             cluster_add! of x[t-1] (src/pmdi.jl:300) and calc_logprob of x[t]
-//                             in the same pass over the row;
-//               plain item  = calc_logprob of `qb` blocks of any other occupied row
-//                             (src/pmdi.jl:218-220);
-//             the warp that finishes the last item of a unit runs the unit's proposal
-//             (src/pmdi.jl:223-265: softmax-cdf, draw, weight increment) -> lab/inc[t&1][k][slot]
-//             - provided step t-1 is RESOLVED: its grid barrier has completed and one warp has
-//             folded every particle's increments and the Phi coupling (src/misc.jl:50-59) into
-//             the CTA's private log-weights and evaluated calc_ESS (src/misc.jl:15-25; identical
-//             bits in every CTA, so all CTAs take the same branch).  Units that finish earlier
-//             are deferred to the end of the queue;
-//   arrive    at the grid barrier of step t (no wait).
-// Resampling (draw_partstar src/misc.jl:27-47 by CTA 0, then all CTAs move the duplicated
-// particles' rows) costs two blocking grid barriers and happens on a few steps per sweep.
+// Ownership.  A CTA owns a fixed set of particle SLOTS for the whole sweep - all K datasets of a
+// slot, i.e. K units of sufficient statistics - so predictive, proposal, add and the particle's
+// weight update are CTA-local.  Per observation step only the ESS test needs the grid, and it
+// needs three numbers per CTA.
+//
+// Work.  A unit cycles  items(t) -> proposal(t) -> items(t+1) -> ...  independently of the other
+// units of its CTA.  Items are handed to the CTA's 16 warps through per-step queues in shared
+// memory (ticket = atomicAdd):
+//   fused item  = one 256-feature block of the row the particle chose in step t-1: cluster_add!
+//                 of x[t-1] (src/pmdi.jl:300) and calc_logprob of x[t] in one pass over the row;
+//   plain item  = calc_logprob of `qb` blocks of any other occupied row (src/pmdi.jl:218-220).
+// The warp that finishes the last item of a unit runs the unit's proposal (src/pmdi.jl:223-265:
+// softmax-cdf, draw, weight increment) and at once appends the unit's items for step t+1 to the
+// next queue, so other warps stream them while the slower units of step t are still going.  The
+// warp whose proposal is the K-th of a particle folds the increments and the Phi coupling
+// (src/misc.jl:50-59) into the particle's log-weight; the warp that completes the CTA's last
+// particle publishes the CTA's (max, sum w, sum w^2), issues the TMA bulk copy of a later
+// observation row into the 4-deep shared-memory ring (mbarrier-tracked) and ARRIVES at the grid
+// counter - nobody waits there.
+//
+// The one gate: proposal(t+1) of any unit needs step t RESOLVED - every CTA has arrived and one
+// warp of this CTA has combined the partials into calc_ESS (src/misc.jl:15-25; same bits in
+// every CTA, so all CTAs take the same branch).  Units that get there early are parked and picked
+// up by idle warps.  On the rare resampling step (ESS <= P/2) the CTA drains the queue (which
+// applies the pending adds), all warps meet, CTA 0 runs draw_partstar (src/misc.jl:27-47), all
+// CTAs move the duplicated particles' rows (two blocking grid barriers), and the step restarts.
 #pragma once
 #include "cluster_types.cuh"
-
-struct SweepSmem {
-  double red[3 * 32];
-  double lp_empty[PMDI_MAX_K];  // predictive of the empty cluster, this step
-  double res_mx;                // max log-weight of the last resolved step
-  int item_ctr, total_items, n_fused, n_defer;
-  int res_step;   // last step whose weights / ESS this CTA has folded in
-  int res_claim;  // step a warp has claimed to resolve
-  int res_flag;   // ESS <= P/2 at res_step: resample before going on
-  int fail;
-  unsigned rows_eval[PMDI_MAX_K];
-  unsigned long long tacc[8];
-  unsigned long long t_prev;
-};
-
-// ---- block-wide helpers (fixed shapes -> identical bits in every CTA) -------------------------
-__device__ __forceinline__ double block_max(double v, double* red) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  v = warp_max(v);
-  __syncthreads();
-  if (lane == 0) red[w] = v;
-  __syncthreads();
-  double r = red[lane < (PMDI_NT / 32) ? lane : 0];
-  return warp_max(r);
-}
-__device__ __forceinline__ void block_sum2(double& a, double& b, double* red) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  a = warp_sum(a);
-  b = warp_sum(b);
-  __syncthreads();
-  if (lane == 0) { red[w] = a; red[32 + w] = b; }
-  __syncthreads();
-  double ra = lane < (PMDI_NT / 32) ? red[lane] : 0.0;
-  double rb = lane < (PMDI_NT / 32) ? red[32 + lane] : 0.0;
-  a = warp_sum(ra);
-  b = warp_sum(rb);
-}
 
 // exclusive scan of in[0..P) (global scratch, CTA-local use) into out; returns the total.
 __device__ int block_excl_scan(const int* in, int* out, int P, int* s_tmp /* PMDI_NT+1 ints */) {
@@ -200,241 +162,104 @@ __device__ __noinline__ void trace_mark(const SweepParams& sp, int step, unsigne
     }
   }
 }
+#define TRACE(step_, tag_) if (sp.trace) trace_mark(sp, (step_), (tag_));
+
+#define PMDI_OBS_RING 4
+#define PMDI_ITEM_FUSED 0x80000000u
+#define PMDI_ITEM_INVALID 0xFFFFFFFFu
+
+// one per step parity
+struct StepQ {
+  int head;       // tickets handed out
+  int tail;       // item slots reserved
+  int units_in;   // units that have appended their items (== nu: the list is closed)
+  int part_tail;  // partial-sum slots reserved
+  int left;       // warps that are done with this list
+  int gen;        // the step this buffer serves
+  int pdone;      // particles of this CTA whose weight is folded for this step
+  int pad;
+  unsigned long long ep;  // grid-counter value that completes this step's barrier
+};
+
+struct SweepSmem {
+  StepQ q[2];
+  unsigned long long obs_bar[PMDI_OBS_RING];  // mbarriers of the observation ring
+  unsigned long long epoch;                   // arrivals this CTA has made, times G
+  double res_mx;  // max log-weight over all particles at res_step
+  int res_step;   // last step whose ESS this CTA knows
+  int res_claim;  // step a warp has claimed to resolve
+  int res_flag;   // ESS <= P/2 at res_step: resample before going on
+  int arrived;    // last step this CTA has arrived for
+  int fail;
+  int ev;         // resampling events so far
+  unsigned rows_eval[PMDI_MAX_K];
+  unsigned long long tacc[8];
+};
 
 // per-CTA views into dynamic shared memory
 struct CtaTables {
   unsigned* urow;   // [max_units][N]   occupied rows of a unit: label | n << 8
   int* ucount;      // [max_units]      number of occupied rows
-  int* foff;        // [max_units + 1]  first fused item of a unit in this step's list
-  int* poff;        // [max_units + 1]  first plain item of a unit (after all fused items)
-  int* pbase;       // [max_units]      first partial-sum slot of a unit (rows x J slots)
-  int* uinfo;       // [max_units]      k << 24 | slot
+  int* uinfo;       // [max_units]      k << 24 | slot     (unit u = local slot * K + k)
   int* ulog;        // [max_units]      logical particle of the unit's slot (RNG address, log index)
   int* pend;        // [max_units]      pending add: label | n_after << 8, or -1
   int* pe;          // [max_units]      position of the pending row in urow
-  int* remaining;   // [max_units]      items of the unit not yet finished this step
-  int* defer;       // [max_units]      units whose proposal waits for the previous step's weights
-  unsigned* items;  // [item_cap]       fused << 31 | u << 13 | e << 5 | j0
-  double* part;     // [item_cap]       predictive partial sums of this step
+  int* ustate;      // [max_units]      0, or 1 + step: all items of that step done, proposal parked
+  int* remaining;   // [2][max_units]   items of the unit not yet finished, per step parity
+  int* pbase;       // [2][max_units]   first partial-sum slot of the unit, per step parity
+  unsigned* items;  // [2][item_cap]    fused << 31 | u << 13 | e << 5 | j0, or INVALID
+  double* part;     // [2][item_cap]    predictive partial sums
   double* lp_s;     // [NW][Npad]       per-warp proposal scratch
   double* Pi_s;     // [K][N]
+  double* lw_s;     // [max_slots]      log-weight of the owned particles
+  double* inc_s;    // [2][max_slots*K] this step's weight increments
+  int* lab_s;       // [2][max_slots*K] this step's labels
+  int* pcount;      // [2][max_slots]   proposals of the particle done this step
+  int MU, cap;
 };
-
-#define PMDI_ITEM_FUSED 0x80000000u
-
-// cluster_add! of the pending row of every unit against observation buffer xb (only after the
-// last observation: every other pending add is applied by the next step's fused items).
-__device__ __noinline__ void flush_adds(const SweepParams& sp, const CtaTables& T, int nu, const unsigned char* xb,
-                                        const double* lf) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = PMDI_NT / 32, N = sp.N;
-#pragma unroll 1
-  for (int it = warp; it < nu * sp.Jmax; it += NW) {
-    const int u = it / sp.Jmax, j = it - u * sp.Jmax;
-    const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
-    const DsDev& ds = sp.ds[k];
-    if (j >= ds.J || T.pend[u] < 0) continue;
-    const int label = T.pend[u] & 0xFF, n = T.pend[u] >> 8;
-    const long long row = (long long)slot * N + label;
-    if (ds.type == T_GAUSSIAN) gauss_add_block(ds, row, j, n, (const double*)(xb + ds.x_off), lane);
-    else if (ds.type == T_CATEGORICAL) cat_add_block(ds, row, j, (const int*)(xb + ds.x_off), lane);
-    else nb_add_block(ds, row, j, n, (const int*)(xb + ds.x_off), lane, lf, sp.lf_T);
-  }
-  __syncthreads();
-#pragma unroll 1
-  for (int u = threadIdx.x; u < nu; u += PMDI_NT) T.pend[u] = -1;
-}
-
-// Proposal for one unit (dataset k, particle slot), by one warp: src/pmdi.jl:223-265.
-// Written for code size (it runs once per unit per step between long streaming items and must
-// not fall out of the instruction cache): label-indexed scratch in shared memory, plain loops.
-__device__ __noinline__ void propose_unit(const SweepParams& sp, const CtaTables& T, int u, int step,
-                                          const double* lp_empty_s, unsigned* rows_eval_s) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int K = sp.K, N = sp.N, P = sp.P, par = step & 1;
-  const int Npad = (N + 31) & ~31;
-  const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
-  const DsDev& ds = sp.ds[k];
-  const int p = T.ulog[u];
-  double* lps = T.lp_s + (size_t)warp * Npad;  // lp[label], then f[label], then cumsum[label]
-  const double lpe = lp_empty_s[k];
-  const int cnt = T.ucount[u];
-  const int fe = T.pend[u] >= 0 ? T.pe[u] : -1;  // the row that ran as fused items: one partial per block
-  const double* part = T.part + T.pbase[u];
-  const unsigned* urow = T.urow + (size_t)u * N;
-  const int J = ds.J, qb = sp.qb;
-#pragma unroll 1
-  for (int m = lane; m < N; m += 32) lps[m] = lpe;
-  __syncwarp();
-#pragma unroll 1
-  for (int e = lane; e < cnt; e += 32) {
-    const unsigned ent = urow[e];
-    double a = __ldg(ds.rc + (ent >> 8));
-    const int stride = (e == fe) ? 1 : qb;
-#pragma unroll 1
-    for (int j = 0; j < J; j += stride) a += part[e * J + j];
-    lps[ent & 0xFF] = a;
-  }
-  __syncwarp();
-  double mx = -INFINITY;
-#pragma unroll 1
-  for (int m = lane; m < N; m += 32) {
-    const double v = lps[m];
-    mx = fmax(mx, v);
-    if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = v;
-  }
-  mx = warp_max(mx);
-  // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
-#pragma unroll 1
-  for (int m = lane; m < N; m += 32) lps[m] = pm_exp(lps[m] - mx) * T.Pi_s[k * N + m];
-  __syncwarp();
-  if (lane == 0) {
-    double run = 0.0;
-#pragma unroll 1
-    for (int m = 0; m < N; ++m) { run += lps[m]; lps[m] = run; }
-  }
-  __syncwarp();
-  const double tot = lps[N - 1];
-  const double inc = pm_log(tot) + mx;
-  int label;
-  if (p == 0) {
-    label = (int)sp.s_in[(size_t)k * sp.n_obs + sp.order[sp.n1 - 1 + step]] - 1;  // reference trajectory (:262)
-  } else {
-    const double uu = sp.tape_alloc ? sp.tape_alloc[((size_t)step * K + k) * P + p]
-                                    : pm_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
-    label = N - 1;
-#pragma unroll 1
-    for (int m0 = 0; m0 < N - 1; m0 += 32) {
-      const int m = m0 + lane;
-      const bool hit = (m < N - 1) && (pm_div(lps[m < N ? m : 0], tot) > uu);  // strict '>' (:255)
-      const unsigned b = __ballot_sync(FULL, hit);
-      if (b) { label = m0 + __ffs(b) - 1; break; }
-    }
-  }
-  // bookkeeping of the chosen row: size, occupied-row list, pending add
-  int pos = -1;
-#pragma unroll 1
-  for (int e0 = 0; e0 < cnt; e0 += 32) {
-    const int e = e0 + lane;
-    const bool hit = (e < cnt) && ((int)(urow[e] & 0xFF) == label);
-    const unsigned b = __ballot_sync(FULL, hit);
-    if (b) { pos = e0 + __ffs(b) - 1; break; }
-  }
-  if (lane == 0) {
-    int n_new = 1;
-    unsigned* urw = T.urow + (size_t)u * N;
-    if (pos >= 0) {
-      const unsigned ent = urw[pos] + (1u << 8);
-      urw[pos] = ent;
-      n_new = (int)(ent >> 8);
-    } else {
-      urw[cnt] = (unsigned)label | (1u << 8);
-      T.ucount[u] = cnt + 1;
-    }
-    ds.n[(long long)slot * N + label] = n_new;
-    T.pend[u] = label | (n_new << 8);
-    T.pe[u] = pos >= 0 ? pos : cnt;
-    sp.lab[((size_t)par * K + k) * P + p] = (uint8_t)label;
-    sp.inc[((size_t)par * K + k) * P + p] = inc;
-    sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
-    if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
-    atomicAdd(&rows_eval_s[k], (unsigned)cnt);
-  }
-  __syncwarp();
-}
-
-// Weights of step `st` by ONE warp: fold every particle's K increments (dataset order, as
-// src/pmdi.jl:210,233) and the Phi coupling (Phi_upweight!, src/misc.jl:50-59) into this CTA's
-// private log-weights, then calc_ESS (src/misc.jl:15-25).  Fixed reduction shape -> identical
-// bits in every CTA.  lab/inc are indexed by LOGICAL particle, so every load of a dataset is
-// independent: 8 particles per lane are in flight per L2 round trip.
-// Returns ESS <= P/2 (src/pmdi.jl:317); *mx_out = max log-weight.
-#define PMDI_RCH 8
-__device__ __noinline__ bool resolve_weights(const SweepParams& sp, int st, double* lw, int cta, double* mx_out) {
-  const int lane = threadIdx.x & 31, K = sp.K, P = sp.P, par = st & 1;
-  const uint8_t* lab_g = sp.lab + (size_t)par * K * P;
-  const double* inc_g = sp.inc + (size_t)par * K * P;
-  double mx = -INFINITY;
-  double w[PMDI_RCH];
-#pragma unroll 1
-  for (int base = 0; base < P; base += 32 * PMDI_RCH) {
-    unsigned long long lb[PMDI_RCH];
-#pragma unroll
-    for (int i = 0; i < PMDI_RCH; ++i) {
-      const int p = base + lane + 32 * i;
-      w[i] = (p < P) ? __ldcg(lw + p) : -INFINITY;
-      lb[i] = 0ull;
-    }
-#pragma unroll 1
-    for (int k = 0; k < K; ++k) {
-      double t[PMDI_RCH];
-      unsigned l8[PMDI_RCH];
-#pragma unroll
-      for (int i = 0; i < PMDI_RCH; ++i) {
-        const int p = base + lane + 32 * i;
-        t[i] = (p < P) ? ldcg_f64(inc_g + (size_t)k * P + p) : 0.0;
-        l8[i] = (p < P) ? (unsigned)ldcg_u8(lab_g + (size_t)k * P + p) : 0u;
-      }
-#pragma unroll
-      for (int i = 0; i < PMDI_RCH; ++i) {
-        w[i] += t[i];
-        lb[i] |= (unsigned long long)l8[i] << (8 * k);
-      }
-    }
-    int idx = 0;
-#pragma unroll 1
-    for (int k1 = 0; k1 < K - 1; ++k1)
-#pragma unroll 1
-      for (int k2 = k1 + 1; k2 < K; ++k2) {
-        const double phil = sp.l1phi[idx++];
-#pragma unroll
-        for (int i = 0; i < PMDI_RCH; ++i)
-          w[i] += (((lb[i] >> (8 * k1)) & 0xFF) == ((lb[i] >> (8 * k2)) & 0xFF)) ? phil : 0.0;
-      }
-#pragma unroll
-    for (int i = 0; i < PMDI_RCH; ++i) {
-      const int p = base + lane + 32 * i;
-      if (p < P) {
-        __stcg(lw + p, w[i]);
-        mx = fmax(mx, w[i]);
-        if (cta == 0 && sp.dbg_lw) sp.dbg_lw[(size_t)st * P + p] = w[i];
-      }
-    }
-  }
-  mx = warp_max(mx);
-  double num = 0.0, den = 0.0;
-#pragma unroll 1
-  for (int base = 0; base < P; base += 32 * PMDI_RCH) {
-    if (P > 32 * PMDI_RCH) {  // otherwise the weights are still in registers
-#pragma unroll
-      for (int i = 0; i < PMDI_RCH; ++i) {
-        const int p = base + lane + 32 * i;
-        w[i] = (p < P) ? __ldcg(lw + p) : -INFINITY;
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < PMDI_RCH; ++i) {
-      const double e = pm_exp(w[i] - mx);  // exp(-inf) = 0 for the padding
-      num += e;
-      den += e * e;
-    }
-  }
-  num = warp_sum(num);
-  den = warp_sum(den);
-  *mx_out = mx;
-  const bool do_res = (num * num) / den <= 0.5 * (double)P;
-  if (!do_res && cta == 0 && lane == 0) sp.ev_of_step[st] = -1;
-  return do_res;
-}
 
 __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
   unsigned long long v;
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_vol(const int* p) { return *(const volatile int*)p; }
+__device__ __forceinline__ void st_vol(int* p, int v) { *(volatile int*)p = v; }
 
-// ---- cold or once-per-step pieces as separate functions (code size, see pm_log) ----------------
+// ---- mbarrier / TMA bulk copy (observation ring) -----------------------------------------------
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok) : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// one thread: bulk-copy the K rows of the observation swept at `step` into ring slot step % 4
+__device__ __noinline__ void issue_obs(const SweepParams& sp, int step, unsigned char* xring, unsigned long long* bars) {
+  if (step >= sp.steps) return;
+  const int b = step % PMDI_OBS_RING;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + b);
+  const int obs = sp.order[sp.n1 - 1 + step];
+  unsigned total = 0;
+#pragma unroll 1
+  for (int k = 0; k < sp.K; ++k) total += (unsigned)sp.ds[k].Dp * (sp.ds[k].type == T_GAUSSIAN ? 8u : 4u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the slot
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+#pragma unroll 1
+  for (int k = 0; k < sp.K; ++k) {
+    const DsDev& ds = sp.ds[k];
+    const unsigned bytes = (unsigned)ds.Dp * (ds.type == T_GAUSSIAN ? 8u : 4u);
+    const unsigned char* src = (const unsigned char*)ds.xstage + (size_t)obs * bytes;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(xring + (size_t)b * sp.sm_x_bytes + ds.x_off);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  }
+}
 
-// spin until the arrival counter reaches `target` (thread 0 of the caller); false = watchdog / error
+// spin until the arrival counter reaches `target` (one thread); false = watchdog / error
 __device__ __noinline__ bool bar_wait(const unsigned long long* bar, unsigned long long target, int* err) {
   const unsigned long long t0 = globaltimer_ns();
   unsigned spins = 0;
@@ -448,17 +273,17 @@ __device__ __noinline__ bool bar_wait(const unsigned long long* bar, unsigned lo
   return true;
 }
 
-// blocking full grid barrier (resampling only)
-__device__ __noinline__ bool grid_sync(unsigned long long* bar, unsigned long long& epoch, int G, int* err, int* s_fail) {
+// blocking full grid barrier (resampling only), all threads of the CTA
+__device__ __noinline__ bool grid_sync(unsigned long long* bar, SweepSmem& sm, int G, int* err) {
   __syncthreads();
-  epoch += G;
   if (threadIdx.x == 0) {
+    sm.epoch += G;
     __threadfence();
     atomicAdd(bar, 1ull);
-    if (!bar_wait(bar, epoch, err)) *s_fail = 1;
+    if (!bar_wait(bar, sm.epoch, err)) sm.fail = 1;
   }
   __syncthreads();
-  return *s_fail == 0;
+  return sm.fail == 0;
 }
 
 // occupied rows (and the logical particle) of every owned unit, from the state in HBM
@@ -483,85 +308,101 @@ __device__ __noinline__ void rebuild_rows(const SweepParams& sp, const CtaTables
   }
 }
 
-// stage (asynchronously) the observation of one step into a ring buffer
-__device__ __noinline__ void prefetch_obs(const SweepParams& sp, int step, unsigned char* xb) {
-  if (step >= sp.steps) return;
-  const int obs = sp.order[sp.n1 - 1 + step];
+// cluster_add! of the pending row of every unit against observation buffer xb (only after the
+// last observation: every other pending add is applied by the next step's fused items).
+__device__ __noinline__ void flush_adds(const SweepParams& sp, const CtaTables& T, int nu, const unsigned char* xb,
+                                        const double* lf) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = PMDI_NT / 32, N = sp.N;
 #pragma unroll 1
-  for (int k = 0; k < sp.K; ++k) {
+  for (int it = warp; it < nu * sp.Jmax; it += NW) {
+    const int u = it / sp.Jmax, j = it - u * sp.Jmax;
+    const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
     const DsDev& ds = sp.ds[k];
-    const int bytes = ds.Dp * (ds.type == T_GAUSSIAN ? 8 : 4);
-    const unsigned char* src = (const unsigned char*)ds.xstage + (size_t)obs * bytes;
-    unsigned char* dst = xb + ds.x_off;
-#pragma unroll 1
-    for (int o = threadIdx.x * 16; o < bytes; o += PMDI_NT * 16) cp_async16(dst + o, src + o);
+    if (j >= ds.J || T.pend[u] < 0) continue;
+    const int label = T.pend[u] & 0xFF, n = T.pend[u] >> 8;
+    const long long row = (long long)slot * N + label;
+    if (ds.type == T_GAUSSIAN) gauss_add_block(ds, row, j, n, (const double*)(xb + ds.x_off), lane);
+    else if (ds.type == T_CATEGORICAL) cat_add_block(ds, row, j, (const int*)(xb + ds.x_off), lane);
+    else nb_add_block(ds, row, j, n, (const int*)(xb + ds.x_off), lane, lf, sp.lf_T);
   }
+  __syncthreads();
 }
 
-// This step's item list, by warp 0: [fused items of all units][plain items of all units], the
-// partial-sum slots of every unit and its item count.  Returns through sm.
-__device__ __noinline__ void build_item_offsets(const SweepParams& sp, const CtaTables& T, int nu, SweepSmem& sm) {
+// number of items / partial-sum slots a unit contributes to a step's list
+__device__ __forceinline__ void unit_item_counts(const SweepParams& sp, const CtaTables& T, int u, int& nI, int& nB) {
+  const int J = sp.ds[T.uinfo[u] >> 24].J, cnt = T.ucount[u], hp = T.pend[u] >= 0 ? 1 : 0;
+  nI = (hp ? J : 0) + (cnt - hp) * ((J + sp.qb - 1) / sp.qb);
+  nB = cnt * J;
+}
+// the unit's items, fused blocks first, written by one warp at items[ib ...]
+__device__ __forceinline__ void write_unit_items(const SweepParams& sp, const CtaTables& T, int u, int nI,
+                                                 unsigned* items) {
   const int lane = threadIdx.x & 31, qb = sp.qb;
-  int runF = 0, runP = 0, runB = 0;
+  const int J = sp.ds[T.uinfo[u] >> 24].J, hp = T.pend[u] >= 0 ? 1 : 0, pe = T.pe[u];
+  const int nF = hp ? J : 0, JQ = (J + qb - 1) / qb;
 #pragma unroll 1
-  for (int ub = 0; ub < nu; ub += 32) {
-    const int u = ub + lane;
-    int cF = 0, cP = 0, cB = 0;
-    if (u < nu) {
-      const int J = sp.ds[T.uinfo[u] >> 24].J, cnt = T.ucount[u], hp = T.pend[u] >= 0 ? 1 : 0;
-      cF = hp ? J : 0;
-      cP = (cnt - hp) * ((J + qb - 1) / qb);
-      cB = cnt * J;
-    }
-    int iF = cF, iP = cP, iB = cB;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int vF = __shfl_up_sync(FULL, iF, o), vP = __shfl_up_sync(FULL, iP, o), vB = __shfl_up_sync(FULL, iB, o);
-      if (lane >= o) { iF += vF; iP += vP; iB += vB; }
-    }
-    if (u < nu) {
-      T.foff[u] = runF + iF - cF; T.poff[u] = runP + iP - cP; T.pbase[u] = runB + iB - cB;
-      T.remaining[u] = cF + cP;
-    }
-    runF += __shfl_sync(FULL, iF, 31); runP += __shfl_sync(FULL, iP, 31); runB += __shfl_sync(FULL, iB, 31);
-  }
-  if (lane == 0) {
-    T.foff[nu] = runF; T.poff[nu] = runP;
-    sm.n_fused = runF;
-    sm.total_items = runF + runP;
-    sm.item_ctr = 0;
-    sm.n_defer = 0;
-    if (runB > sp.item_cap) { atomicExch(sp.err, 78); sm.fail = 1; }
-  }
-}
-
-// decode table: item -> (unit, row entry, first block), all threads
-__device__ __noinline__ void build_item_codes(const SweepParams& sp, const CtaTables& T, int nu, int total, int nF) {
-  const int qb = sp.qb;
-#pragma unroll 1
-  for (int it = threadIdx.x; it < total; it += PMDI_NT) {
-    const bool fz = it < nF;
-    const int* off = fz ? T.foff : T.poff;
-    const int r0 = fz ? it : it - nF;
-    int lo = 0, hi = nu - 1;  // last u with off[u] <= r0
-#pragma unroll 1
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (off[mid] <= r0) lo = mid; else hi = mid - 1;
-    }
-    const int r = r0 - off[lo];
+  for (int i = lane; i < nI; i += 32) {
     unsigned code;
-    if (fz) {
-      code = PMDI_ITEM_FUSED | ((unsigned)lo << 13) | ((unsigned)T.pe[lo] << 5) | (unsigned)r;
+    if (i < nF) {
+      code = PMDI_ITEM_FUSED | ((unsigned)u << 13) | ((unsigned)pe << 5) | (unsigned)i;
     } else {
-      const int JQ = (sp.ds[T.uinfo[lo] >> 24].J + qb - 1) / qb;
+      const int r = i - nF;
       int e = r / JQ;
       const int q = r - e * JQ;
-      if (T.pend[lo] >= 0 && e >= T.pe[lo]) ++e;  // skip the fused row
-      code = ((unsigned)lo << 13) | ((unsigned)e << 5) | (unsigned)(q * qb);
+      if (hp && e >= pe) ++e;  // skip the fused row
+      code = ((unsigned)u << 13) | ((unsigned)e << 5) | (unsigned)(q * qb);
     }
-    T.items[it] = code;
+    *(volatile unsigned*)(items + i) = code;
   }
+}
+
+// (Re)start the queues at step t with the item lists of ALL units (no pending adds): kernel start
+// and after a resampling.  All threads.
+__device__ __noinline__ void init_queues(const SweepParams& sp, const CtaTables& T, SweepSmem& sm, int nu, int ns, int t) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = t & 1;
+  for (int i = tid; i < 2 * T.cap; i += PMDI_NT) T.items[i] = PMDI_ITEM_INVALID;
+  for (int u = tid; u < nu; u += PMDI_NT) { T.pend[u] = -1; T.pe[u] = 0; T.ustate[u] = 0; }
+  for (int i = tid; i < 2 * ns; i += PMDI_NT) T.pcount[i] = 0;
+  __syncthreads();
+  if (warp == 0) {
+    int runI = 0, runB = 0;
+#pragma unroll 1
+    for (int ub = 0; ub < nu; ub += 32) {
+      const int u = ub + lane;
+      int cI = 0, cB = 0;
+      if (u < nu) unit_item_counts(sp, T, u, cI, cB);
+      int iI = cI, iB = cB;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int vI = __shfl_up_sync(FULL, iI, o), vB = __shfl_up_sync(FULL, iB, o);
+        if (lane >= o) { iI += vI; iB += vB; }
+      }
+      if (u < nu) {
+        T.remaining[b * T.MU + u] = cI;
+        T.pbase[b * T.MU + u] = runB + iB - cB;
+        T.remaining[(b ^ 1) * T.MU + u] = runI + iI - cI;  // scratch: first item of the unit
+        if (cI == 0) T.ustate[u] = 1 + t;                   // nothing to evaluate: straight to the proposal
+      }
+      runI += __shfl_sync(FULL, iI, 31);
+      runB += __shfl_sync(FULL, iB, 31);
+    }
+    if (lane == 0) {
+      StepQ& q = sm.q[b];
+      q.head = 0; q.tail = runI; q.units_in = nu; q.part_tail = runB; q.left = 0; q.gen = t; q.pdone = 0;
+      StepQ& q1 = sm.q[b ^ 1];
+      q1.head = 0; q1.tail = 0; q1.units_in = 0; q1.part_tail = 0; q1.left = 0; q1.gen = t + 1; q1.pdone = 0;
+      if (runI > T.cap || runB > T.cap) { atomicExch(sp.err, 78); sm.fail = 1; }
+    }
+  }
+  __syncthreads();
+  if (sm.fail) return;
+#pragma unroll 1
+  for (int u = warp; u < nu; u += PMDI_NT / 32) {
+    int nI, nB;
+    unit_item_counts(sp, T, u, nI, nB);
+    write_unit_items(sp, T, u, nI, T.items + (size_t)b * T.cap + T.remaining[(b ^ 1) * T.MU + u]);
+  }
+  __syncthreads();
 }
 
 // One work item by one warp; returns the predictive partial sum (identical in all lanes).
@@ -596,17 +437,262 @@ __device__ __noinline__ double run_item(const SweepParams& sp, const CtaTables& 
   return nb_eval_item(ds, row, j0, j1, n, (const int*)(xs_cur + ds.x_off), lane, lf, lfT);
 }
 
+// calc_ESS over the whole grid from the per-CTA partials of step `st` (max, sum w, sum w^2 with
+// w = exp(l - max_cta)), by ONE warp; fixed shape -> identical bits in every CTA.
+// Returns ESS <= P/2 (src/pmdi.jl:317); *mx_out = max log-weight.
+__device__ __noinline__ bool resolve_ess(const SweepParams& sp, int st, double* mx_out) {
+  const int lane = threadIdx.x & 31, G = sp.G;
+  const double* ep = sp.ess_part + (size_t)(st & 1) * 3 * G;
+  double mx = -INFINITY;
+#pragma unroll 1
+  for (int c = lane; c < G; c += 32) mx = fmax(mx, ldcg_f64(ep + 3 * c));
+  mx = warp_max(mx);
+  double num = 0.0, den = 0.0;
+#pragma unroll 1
+  for (int c = lane; c < G; c += 32) {
+    const double e = pm_exp(ldcg_f64(ep + 3 * c) - mx);
+    num += ldcg_f64(ep + 3 * c + 1) * e;
+    den += ldcg_f64(ep + 3 * c + 2) * (e * e);
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+  *mx_out = mx;
+  const bool do_res = (num * num) / den <= 0.5 * (double)sp.P;
+  if (!do_res && blockIdx.x == 0 && lane == 0) sp.ev_of_step[st] = -1;
+  return do_res;
+}
+
+// Is step `s` resolved?  Warp-uniform result: 0 not yet, 1 yes (go on), 2 yes and it resamples.
+// The first warp to find the step's grid barrier complete evaluates the ESS.
+__device__ __noinline__ int check_resolved(const SweepParams& sp, SweepSmem& sm, int s) {
+  if (s < 0) return 1;
+  const int lane = threadIdx.x & 31;
+  int r = 0;
+  if (lane == 0) {
+    const int rs = ld_vol(&sm.res_step);
+    if (rs >= s) r = ld_vol(&sm.res_flag) ? 2 : 1;
+    else if (rs == s - 1 && ld_vol(&sm.arrived) >= s &&
+             ld_acquire_u64((const unsigned long long*)sp.bar) >= sm.q[s & 1].ep &&
+             atomicCAS(&sm.res_claim, s - 1, s) == s - 1) r = 3;
+  }
+  r = __shfl_sync(FULL, r, 0);
+  if (r == 3) {
+    __threadfence();
+    TRACE(s + 1, 9)
+    double mxv;
+    const bool res = resolve_ess(sp, s, &mxv);
+    if (lane == 0) {
+      sm.res_mx = mxv;
+      st_vol(&sm.res_flag, res ? 1 : 0);
+      __threadfence_block();
+      st_vol(&sm.res_step, s);
+    }
+    __syncwarp();
+    TRACE(s + 1, 10)
+    r = res ? 2 : 1;
+  }
+  return r;
+}
+
+// The CTA's last particle of step t is folded: publish the CTA's ESS partial, start the copy of a
+// later observation, arrive at the grid counter.  One warp.
+__device__ __noinline__ void cta_arrive(const SweepParams& sp, const CtaTables& T, SweepSmem& sm, int ns, int t,
+                                        unsigned char* xring) {
+  const int lane = threadIdx.x & 31;
+  double m = -INFINITY;
+#pragma unroll 1
+  for (int sl = lane; sl < ns; sl += 32) m = fmax(m, T.lw_s[sl]);
+  m = warp_max(m);
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll 1
+  for (int sl = lane; sl < ns; sl += 32) {
+    const double e = pm_exp(T.lw_s[sl] - m);
+    s1 += e;
+    s2 += e * e;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    double* ep = sp.ess_part + ((size_t)(t & 1) * sp.G + blockIdx.x) * 3;
+    __stcg(ep, m); __stcg(ep + 1, s1); __stcg(ep + 2, s2);
+    issue_obs(sp, t + PMDI_OBS_RING - 1, xring, sm.obs_bar);  // its ring slot held x[t-1]: free now
+    sm.epoch += sp.G;
+    sm.q[t & 1].ep = sm.epoch;
+    __threadfence();
+    st_vol(&sm.arrived, t);
+    atomicAdd((unsigned long long*)sp.bar, 1ull);
+  }
+  __syncwarp();
+}
+
+// Proposal for one unit (dataset k, particle slot) at step `step`, by one warp: src/pmdi.jl:223-265;
+// then the unit's items of the next step, the particle's weight fold, and the CTA's arrival.
+// Written for a short instruction path (it sits between long streaming items).
+__device__ __noinline__ void propose_unit(const SweepParams& sp, const CtaTables& T, SweepSmem& sm, int u, int step,
+                                          int nu, int ns, unsigned char* xring) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = sp.K, N = sp.N, P = sp.P, par = step & 1;
+  const int Npad = (N + 31) & ~31;
+  const int k = T.uinfo[u] >> 24, slot = T.uinfo[u] & 0xFFFFFF;
+  const DsDev& ds = sp.ds[k];
+  const int p = T.ulog[u];
+  double* lps = T.lp_s + (size_t)warp * Npad;  // lp[label], then f[label], then cumsum[label]
+  const double lpe = __ldg(sp.lp_empty + (size_t)step * K + k);
+  const int cnt = T.ucount[u];
+  const int fe = T.pend[u] >= 0 ? T.pe[u] : -1;  // the row that ran as fused items: one partial per block
+  const double* part = T.part + (size_t)par * T.cap + T.pbase[par * T.MU + u];
+  unsigned* urow = T.urow + (size_t)u * N;
+  const int J = ds.J, qb = sp.qb;
+  double uu = 0.0;
+  if (p != 0) uu = sp.tape_alloc ? __ldg(sp.tape_alloc + ((size_t)step * K + k) * P + p)
+                                 : pm_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
+#pragma unroll 1
+  for (int m = lane; m < N; m += 32) lps[m] = lpe;
+  __syncwarp();
+#pragma unroll 1
+  for (int e = lane; e < cnt; e += 32) {
+    const unsigned ent = urow[e];
+    double a = __ldg(ds.rc + (ent >> 8));
+    const int stride = (e == fe) ? 1 : qb;
+#pragma unroll 1
+    for (int j = 0; j < J; j += stride) a += part[e * J + j];
+    lps[ent & 0xFF] = a;
+  }
+  __syncwarp();
+  double mx = -INFINITY;
+#pragma unroll 1
+  for (int m = lane; m < N; m += 32) {
+    const double v = lps[m];
+    mx = fmax(mx, v);
+    if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = v;
+  }
+  mx = warp_max(mx);
+  // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
+#pragma unroll 1
+  for (int m = lane; m < N; m += 32) lps[m] = pm_exp(lps[m] - mx) * T.Pi_s[k * N + m];
+  __syncwarp();
+  if (lane == 0) {
+    double run = 0.0;
+#pragma unroll 1
+    for (int m = 0; m < N; ++m) { run += lps[m]; lps[m] = run; }
+  }
+  __syncwarp();
+  const double tot = lps[N - 1];
+  int label;
+  if (p == 0) {
+    label = (int)sp.s_in[(size_t)k * sp.n_obs + sp.order[sp.n1 - 1 + step]] - 1;  // reference trajectory (:262)
+  } else {
+    label = N - 1;
+#pragma unroll 1
+    for (int m0 = 0; m0 < N - 1; m0 += 32) {
+      const int m = m0 + lane;
+      const bool hit = (m < N - 1) && (pm_div(lps[m < N ? m : 0], tot) > uu);  // strict '>' (:255)
+      const unsigned b = __ballot_sync(FULL, hit);
+      if (b) { label = m0 + __ffs(b) - 1; break; }
+    }
+  }
+  // bookkeeping of the chosen row: size, occupied-row list, pending add
+  int pos = -1;
+#pragma unroll 1
+  for (int e0 = 0; e0 < cnt; e0 += 32) {
+    const int e = e0 + lane;
+    const bool hit = (e < cnt) && ((int)(urow[e] & 0xFF) == label);
+    const unsigned b = __ballot_sync(FULL, hit);
+    if (b) { pos = e0 + __ffs(b) - 1; break; }
+  }
+  if (lane == 0) {
+    int n_new = 1;
+    if (pos >= 0) {
+      const unsigned ent = urow[pos] + (1u << 8);
+      urow[pos] = ent;
+      n_new = (int)(ent >> 8);
+    } else {
+      urow[cnt] = (unsigned)label | (1u << 8);
+      T.ucount[u] = cnt + 1;
+    }
+    ds.n[(long long)slot * N + label] = n_new;
+    T.pend[u] = label | (n_new << 8);
+    T.pe[u] = pos >= 0 ? pos : cnt;
+    sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
+    if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
+    atomicAdd(&sm.rows_eval[k], (unsigned)cnt);
+  }
+  __syncwarp();
+  // ---- the unit's items of step + 1 go to the other queue right away
+  {
+    StepQ& qn = sm.q[par ^ 1];
+    const int nb = par ^ 1;
+    int ib = 0, nI = 0, nB = 0;
+    if (lane == 0) {
+      while (ld_vol(&qn.gen) != step + 1 && !ld_vol(&sm.fail)) __nanosleep(32);
+      if (step + 1 < sp.steps) {
+        unit_item_counts(sp, T, u, nI, nB);
+        ib = atomicAdd(&qn.tail, nI);
+        const int pb = atomicAdd(&qn.part_tail, nB);
+        T.remaining[nb * T.MU + u] = nI;
+        T.pbase[nb * T.MU + u] = pb;
+        if (ib + nI > T.cap || pb + nB > T.cap) { atomicExch(sp.err, 78); st_vol(&sm.fail, 1); nI = 0; }
+      }
+      __threadfence_block();
+    }
+    ib = __shfl_sync(FULL, ib, 0);
+    nI = __shfl_sync(FULL, nI, 0);
+    if (nI > 0) write_unit_items(sp, T, u, nI, T.items + (size_t)nb * T.cap + ib);
+    __threadfence_block();
+    __syncwarp();
+    if (lane == 0) atomicAdd(&qn.units_in, 1);
+  }
+  // ---- weight increment; the K-th proposal of the particle folds its log-weight
+  const double inc = pm_log(tot) + mx;
+  int last_particle = 0;
+  if (lane == 0) {
+    const int sl = u / K;
+    T.inc_s[(par * ns + sl) * K + k] = inc;
+    T.lab_s[(par * ns + sl) * K + k] = label;
+    __threadfence_block();
+    if (atomicAdd(&T.pcount[par * ns + sl], 1) == K - 1) {
+      __threadfence_block();
+      T.pcount[par * ns + sl] = 0;
+      const volatile double* iv = T.inc_s + (size_t)(par * ns + sl) * K;
+      const volatile int* lv = T.lab_s + (size_t)(par * ns + sl) * K;
+      double w = T.lw_s[sl];
+#pragma unroll 1
+      for (int kk = 0; kk < K; ++kk) w += iv[kk];  // dataset order, as src/pmdi.jl:210,233
+      int idx = 0;
+#pragma unroll 1
+      for (int k1 = 0; k1 < K - 1; ++k1)
+#pragma unroll 1
+        for (int k2 = k1 + 1; k2 < K; ++k2) {  // Phi_upweight! (src/misc.jl:50-59)
+          w += (lv[k1] == lv[k2]) ? sp.l1phi[idx] : 0.0;
+          ++idx;
+        }
+      T.lw_s[sl] = w;
+      __stcg(sp.lw + p, w);
+      if (sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
+      __threadfence_block();
+      last_particle = (atomicAdd(&sm.q[par].pdone, 1) == ns - 1) ? 1 : 0;
+    }
+  }
+  last_particle = __shfl_sync(FULL, last_particle, 0);
+  if (last_particle) {
+    if (lane == 0) sm.q[par].pdone = 0;
+    __threadfence_block();
+    TRACE(step, 7)
+    cta_arrive(sp, T, sm, ns, step, xring);
+  }
+}
+
 // Resampling after step `st` (draw_partstar src/misc.jl:27-47 by CTA 0, then every CTA moves the
 // duplicated particles' rows, src/pmdi.jl:318-341 in dense form): two blocking grid barriers.
-__device__ __noinline__ bool do_resample(const SweepParams& sp, const CtaTables& T, int nu, int st, int& ev,
-                                         unsigned long long& epoch, double mx, double* lw, int* s_tmp, int* s_fail) {
+// All threads of the CTA; every pending add has been applied.
+__device__ __noinline__ bool do_resample(const SweepParams& sp, const CtaTables& T, SweepSmem& sm, int nu, int ns,
+                                         int st, int* s_tmp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = PMDI_NT / 32;
-  const int cta = blockIdx.x, G = sp.G, K = sp.K, N = sp.N, P = sp.P;
+  const int cta = blockIdx.x, G = sp.G, K = sp.K, N = sp.N;
   unsigned long long* bar = (unsigned long long*)sp.bar;
-#pragma unroll 1
-  for (int u = tid; u < nu; u += PMDI_NT) T.pend[u] = -1;
-  if (cta == 0) resample_plan(sp, st, ev, mx, lw, s_tmp);
-  if (!grid_sync(bar, epoch, G, sp.err, s_fail)) return false;
+  const int ev = sm.ev;
+  if (cta == 0) resample_plan(sp, st, ev, sm.res_mx, sp.lw, s_tmp);
+  if (!grid_sync(bar, sm, G, sp.err)) return false;
   const int ncopy = ldcg_i32(sp.plan_out);
   const int gw = cta * NW + warp, GW = G * NW;
 #pragma unroll 1
@@ -616,227 +702,258 @@ __device__ __noinline__ bool do_resample(const SweepParams& sp, const CtaTables&
     const int2 cp = __ldcg(sp.copies + c);
     row_copy(sp.ds[k], (long long)cp.x * N + m, (long long)cp.y * N + m, lane);
   }
-#pragma unroll 1
-  for (int p = tid; p < P; p += PMDI_NT) __stcg(lw + p, 1.0);  // logweight .= 1.0 (src/pmdi.jl:319)
+  for (int sl = tid; sl < ns; sl += PMDI_NT) T.lw_s[sl] = 1.0;  // logweight .= 1.0 (src/pmdi.jl:319)
   if (cta == 0 && tid == 0) { sp.counters[0] += 1; sp.counters[1] += ncopy; }
-  ++ev;
-  if (!grid_sync(bar, epoch, G, sp.err, s_fail)) return false;
-  rebuild_rows(sp, T, nu, ev);
+  if (!grid_sync(bar, sm, G, sp.err)) return false;
+  if (tid == 0) sm.ev = ev + 1;
+  rebuild_rows(sp, T, nu, ev + 1);
   __syncthreads();
   return true;
 }
 
 extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_constant__ SweepParams sp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ SweepSmem sm;
+  __shared__ __align__(16) SweepSmem sm;
   __shared__ int s_tmp[PMDI_NT + 2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int NW = PMDI_NT / 32;
-  const int cta = blockIdx.x, G = sp.G;
-  const int K = sp.K, N = sp.N, P = sp.P;
+  const int cta = blockIdx.x;
+  const int K = sp.K, N = sp.N, steps = sp.steps;
   const int Npad = (N + 31) & ~31;
 
-  // dynamic shared memory: [3 x observation][lf table][lp scratch][Pi][part][items][unit tables]
-  unsigned char* xbuf[3] = {smem_raw, smem_raw + sp.sm_x_bytes, smem_raw + 2 * (size_t)sp.sm_x_bytes};
-  double* lf = (double*)(smem_raw + 3 * (size_t)sp.sm_x_bytes);
+  // dynamic shared memory: [4 x observation][lf table][lp scratch][Pi][lw][inc][part x2][items x2][tables]
+  unsigned char* xring = smem_raw;
+  double* lf = (double*)(smem_raw + (size_t)PMDI_OBS_RING * sp.sm_x_bytes);
+  const int u0 = sp.cta_off[cta], nu = sp.cta_off[cta + 1] - u0;
+  const int ns = nu / K;  // particle slots owned by this CTA
+  const int MU = sp.max_units, MS = MU / K;
   CtaTables T;
+  T.MU = MU; T.cap = sp.item_cap;
   T.lp_s = lf + sp.lf_T;
   T.Pi_s = T.lp_s + (size_t)NW * Npad;
-  T.part = T.Pi_s + (size_t)K * N;
-  T.items = (unsigned*)(T.part + sp.item_cap);
-  T.urow = T.items + sp.item_cap;
-  const int u0 = sp.cta_off[cta], nu = sp.cta_off[cta + 1] - u0;
-  const int MU = sp.max_units;
+  T.lw_s = T.Pi_s + (size_t)K * N;
+  T.inc_s = T.lw_s + MS;
+  T.part = T.inc_s + 2 * (size_t)MU;
+  T.items = (unsigned*)(T.part + 2 * (size_t)T.cap);
+  T.urow = T.items + 2 * (size_t)T.cap;
   T.ucount = (int*)(T.urow + (size_t)MU * N);
-  T.foff = T.ucount + MU;
-  T.poff = T.foff + MU + 1;
-  T.pbase = T.poff + MU + 1;
-  T.uinfo = T.pbase + MU;
+  T.uinfo = T.ucount + MU;
   T.ulog = T.uinfo + MU;
   T.pend = T.ulog + MU;
   T.pe = T.pend + MU;
-  T.remaining = T.pe + MU;
-  T.defer = T.remaining + MU;
+  T.ustate = T.pe + MU;
+  T.remaining = T.ustate + MU;
+  T.pbase = T.remaining + 2 * MU;
+  T.lab_s = T.pbase + 2 * MU;
+  T.pcount = T.lab_s + 2 * MU;
   const int lfT = sp.lf_T;
   for (int i = tid; i < lfT; i += PMDI_NT) lf[i] = sp.lf_glob[i];
   for (int i = tid; i < K * N; i += PMDI_NT) T.Pi_s[i] = sp.Pi[i];
+  for (int sl = tid; sl < ns; sl += PMDI_NT) T.lw_s[sl] = sp.lw_init;
   if (tid < PMDI_MAX_K) sm.rows_eval[tid] = 0;
-  for (int u = tid; u < nu; u += PMDI_NT) { T.uinfo[u] = sp.cta_units[u0 + u]; T.pend[u] = -1; T.pe[u] = 0; }
-  if (tid == 0) { sm.res_step = -1; sm.res_claim = -1; sm.res_flag = 0; sm.n_defer = 0; sm.fail = 0; }
-
-  double* lw = sp.lw + (size_t)cta * P;  // this CTA's private copy of the log-weights (L2)
-  for (int p = tid; p < P; p += PMDI_NT) __stcg(lw + p, sp.lw_init);
-
-  unsigned long long* bar = (unsigned long long*)sp.bar;
-  unsigned long long epoch = 0;  // arrivals this CTA has made, times G
-  int ev = 0;
-  const bool timing = sp.phase_ns != nullptr && tid == 0;
-  if (timing) {
-    for (int i = 0; i < 8; ++i) sm.tacc[i] = 0;
-    sm.t_prev = globaltimer_ns();
+  if (tid < 8) sm.tacc[tid] = 0;
+  for (int u = tid; u < nu; u += PMDI_NT) T.uinfo[u] = sp.cta_units[u0 + u];
+  if (tid == 0) {
+    sm.res_step = -1; sm.res_claim = -1; sm.res_flag = 0; sm.arrived = -1; sm.fail = 0; sm.ev = 0;
+    sm.epoch = 0; sm.res_mx = 0.0;
+    for (int b = 0; b < PMDI_OBS_RING; ++b) mbar_init(&sm.obs_bar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-#define PHASE_MARK(i_)                                   \
-  if (timing) {                                          \
-    const unsigned long long now_ = globaltimer_ns();    \
-    sm.tacc[i_] += now_ - sm.t_prev;                     \
-    sm.t_prev = now_;                                    \
-  }
-#define TRACE(tag_) if (sp.trace) trace_mark(sp, step, (tag_));
-  __syncthreads();  // uinfo is visible to every warp
-  rebuild_rows(sp, T, nu, ev);
-  prefetch_obs(sp, 0, xbuf[0]);
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < PMDI_OBS_RING - 1; ++s) issue_obs(sp, s, xring, sm.obs_bar);
+  rebuild_rows(sp, T, nu, 0);
+  __syncthreads();
+  init_queues(sp, T, sm, nu, ns, 0);
+  if (sm.fail) return;
 
-  unsigned long long ep_prev = 0;  // epoch that completes the barrier of the previous step
-  for (int step = 0; step < sp.steps; ++step) {
-    const unsigned char* xs_cur = xbuf[step % 3];
-    const unsigned char* xs_prev = xbuf[(step + 2) % 3];
-    bool first_pass = true;
-  redo_step:
-    TRACE(1)
-    if (first_pass) {
-      cp_async_commit_wait_all();   // this step's observation has landed (own copies)
-      __syncthreads();              // ... everybody's; last step's proposals are complete
-      prefetch_obs(sp, step + 1, xbuf[(step + 1) % 3]);
-    }
-    if (tid < K) sm.lp_empty[tid] = sp.lp_empty[(size_t)step * K + tid];
-    if (warp == 0) build_item_offsets(sp, T, nu, sm);
-    __syncthreads();
-    if (sm.fail) return;  // the other CTAs leave through the barrier's error check
-    const int total = sm.total_items;
-    build_item_codes(sp, T, nu, total, sm.n_fused);
-    __syncthreads();
-    PHASE_MARK(0)
-    TRACE(2)
-    // ------------------------------------------------------------------ the item queue
+  const bool timing = sp.phase_ns != nullptr;
+  unsigned long long tw_prev = timing ? globaltimer_ns() : 0ull;
+#define PHASE_MARK(i_)                                                 \
+  if (timing && lane == 0) {                                           \
+    const unsigned long long now_ = globaltimer_ns();                  \
+    atomicAdd(&sm.tacc[i_], now_ - tw_prev);                           \
+    tw_prev = now_;                                                    \
+  }
+
+  int t = 0;        // the step whose list this warp is working on
+  int obs_ok = -1;  // observations this warp has seen land
+  while (t <= steps) {
+    StepQ& q = sm.q[t & 1];
+    // ---- get a ticket for step t's list, then wait for the item (or for the list to close)
+    unsigned code = PMDI_ITEM_INVALID;
+    int what = 0;  // 1 run item, 2 leave the list, 3 resampling rendezvous, 4 abort
+    int h = -1;
+    unsigned idle_spins = 0;
+    unsigned long long idle_t0 = 0;
     for (;;) {
-      int it = 0;
-      if (lane == 0) it = atomicAdd(&sm.item_ctr, 1);
-      it = __shfl_sync(FULL, it, 0);
-      if (it >= total) break;
-      const unsigned code = T.items[it];
-      TRACE(0x100 | (code & 31) | (((code >> 5) & 7) << 5) | ((T.uinfo[(code >> 13) & 0x3FFFF] >> 24) << 12) | ((code >> 31) << 11))
-      const double v = run_item(sp, T, code, xs_cur, xs_prev, lf);
-      TRACE(3)
-      const int u = (code >> 13) & 0x3FFFF;
-      int act = 0;  // 0 nothing, 1 propose, 2 defer, 3 resolve the previous step first
       if (lane == 0) {
-        T.part[T.pbase[u] + ((code >> 5) & 0xFF) * sp.ds[T.uinfo[u] >> 24].J + (code & 31)] = v;
-        __threadfence_block();
-        if (atomicSub(&T.remaining[u], 1) == 1) {  // this warp finished the unit
-          const int rs = *(volatile int*)&sm.res_step;
-          if (rs >= step - 1) act = (*(volatile int*)&sm.res_flag) ? 0 : 1;
-          else if (rs == step - 2 && ld_acquire_u64(bar) >= ep_prev &&
-                   atomicCAS(&sm.res_claim, step - 2, step - 1) == step - 2) act = 3;
-          else act = 2;
+        what = 0;
+        if (((++idle_spins) & 0xffu) == 0) {  // watchdog: a lost CTA / warp becomes an error, not a hang
+          const unsigned long long now = globaltimer_ns();
+          if (idle_t0 == 0) idle_t0 = now;
+          if (__ldcg(sp.err) != 0) st_vol(&sm.fail, 1);
+          else if (now - idle_t0 > 4000000000ull) { atomicExch(sp.err, 79); st_vol(&sm.fail, 1); }
+        }
+        if (ld_vol(&sm.fail)) what = 4;
+        else if (ld_vol(&sm.res_flag) && t == ld_vol(&sm.res_step) + 2) what = 3;
+        else if (ld_vol(&q.gen) == t) {
+          if (h < 0) h = atomicAdd(&q.head, 1);
+          if (h < T.cap) code = *(volatile unsigned*)(T.items + (size_t)(t & 1) * T.cap + h);
+          if (code != PMDI_ITEM_INVALID) {
+            *(volatile unsigned*)(T.items + (size_t)(t & 1) * T.cap + h) = PMDI_ITEM_INVALID;
+            what = 1;
+          } else if (ld_vol(&q.units_in) == nu && h >= ld_vol(&q.tail)) {
+            what = 2;
+          }
         }
       }
-      act = __shfl_sync(FULL, act, 0);
-      if (act == 3) {
-        __threadfence();
-        TRACE(9)
-        double mxv;
-        const bool r = resolve_weights(sp, step - 1, lw, cta, &mxv);
+      what = __shfl_sync(FULL, what, 0);
+      if (what) break;
+      // ---- idle: a parked unit whose gate has opened?
+      // the parked unit of the EARLIEST step: parked units can be one step apart (one still waiting
+      // to be picked up with its gate open, others already through the next step's items), and
+      // only the earlier one can make progress
+      int pu = -1, pstep = 0;
+      {
+        int best = 0x7fffffff, best_u = -1;
+#pragma unroll 1
+        for (int ub = 0; ub < nu; ub += 32) {
+          const int u = ub + lane;
+          const int st = (u < nu) ? ld_vol(&T.ustate[u]) : 0;
+          if (st != 0 && st < best) { best = st; best_u = u; }
+        }
+        int mn = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mn = min(mn, __shfl_xor_sync(FULL, mn, o));
+        if (mn != 0x7fffffff) {
+          const unsigned b = __ballot_sync(FULL, best == mn);
+          pu = __shfl_sync(FULL, best_u, __ffs(b) - 1);
+          pstep = mn - 1;
+        }
+      }
+      if (pu >= 0) {
+        const int r = check_resolved(sp, sm, pstep - 1);
+        if (r) {
+          int won = 0;
+          if (lane == 0) won = atomicCAS(&T.ustate[pu], pstep + 1, 0) == pstep + 1;
+          won = __shfl_sync(FULL, won, 0);
+          if (won && r == 1) {
+            PHASE_MARK(0)
+            TRACE(pstep, 4)
+            propose_unit(sp, T, sm, pu, pstep, nu, ns, xring);
+            TRACE(pstep, 5)
+            PHASE_MARK(2)
+          }
+        } else {
+          __nanosleep(100);
+        }
+      } else {
+        __nanosleep(40);
+      }
+    }
+    PHASE_MARK(0)
+    if (what == 4) {
+      if (lane == 0 && sp.wd_state) {  // post-mortem of a watchdog: where every warp was
+        int* w = sp.wd_state + ((size_t)cta * NW + warp) * 16;
+        w[0] = t; w[1] = h; w[2] = q.gen; w[3] = q.head; w[4] = q.tail; w[5] = q.units_in; w[6] = q.left;
+        w[7] = sm.res_step; w[8] = sm.res_flag; w[9] = sm.arrived; w[10] = sm.res_claim; w[11] = nu;
+        int parked = 0;
+        for (int u = 0; u < nu; ++u) parked += T.ustate[u] != 0;
+        w[12] = parked; w[13] = sm.q[(t & 1) ^ 1].gen; w[14] = sm.q[(t & 1) ^ 1].units_in; w[15] = sm.q[t & 1].pdone;
+      }
+      return;
+    }
+    if (what == 1) {
+      code = __shfl_sync(FULL, code, 0);
+      __threadfence_block();  // the item's rows were written by other warps of this CTA
+      if (obs_ok < t) {  // x[t] (and x[t-1] before it) have landed in the ring
         if (lane == 0) {
-          sm.res_mx = mxv;
-          sm.res_flag = r ? 1 : 0;
+#pragma unroll 1
+          for (int s = max(obs_ok + 1, t - 1); s <= t; ++s)
+            while (!mbar_try_wait(&sm.obs_bar[s % PMDI_OBS_RING], (unsigned)(s / PMDI_OBS_RING) & 1u)) {}
+        }
+        __syncwarp();
+        obs_ok = t;
+      }
+      TRACE(t, 0x100 | (code & 31) | (((code >> 5) & 7) << 5) | ((T.uinfo[(code >> 13) & 0x3FFFF] >> 24) << 12) | ((code >> 31) << 11))
+      const double v = run_item(sp, T, code, xring + (size_t)(t % PMDI_OBS_RING) * sp.sm_x_bytes,
+                                xring + (size_t)((t + PMDI_OBS_RING - 1) % PMDI_OBS_RING) * sp.sm_x_bytes, lf);
+      TRACE(t, 3)
+      PHASE_MARK(1)
+      const int u = (code >> 13) & 0x3FFFF;
+      int last = 0;
+      if (lane == 0) {
+        const int b = t & 1;
+        T.part[(size_t)b * T.cap + T.pbase[b * MU + u] + ((code >> 5) & 0xFF) * sp.ds[T.uinfo[u] >> 24].J + (code & 31)] = v;
+        __threadfence_block();
+        last = atomicSub(&T.remaining[b * MU + u], 1) == 1;
+      }
+      last = __shfl_sync(FULL, last, 0);
+      if (last) {  // this warp finished the unit's items of step t
+        __threadfence_block();
+        const int r = check_resolved(sp, sm, t - 1);
+        if (r == 1) {
+          TRACE(t, 4)
+          propose_unit(sp, T, sm, u, t, nu, ns, xring);
+          TRACE(t, 5)
+          PHASE_MARK(2)
+        } else if (r == 0) {
+          if (lane == 0) st_vol(&T.ustate[u], 1 + t);  // parked until step t-1 is resolved
+        }
+      }
+      continue;
+    }
+    if (what == 2) {  // done with step t's list
+      TRACE(t, 6)
+      if (lane == 0) {
+        if (atomicAdd(&q.left, 1) == NW - 1) {  // last warp out: the buffer now serves step t + 2
+          q.head = 0; q.tail = 0; q.units_in = 0; q.part_tail = 0; q.left = 0;
           __threadfence_block();
-          *(volatile int*)&sm.res_step = step - 1;
+          st_vol(&q.gen, t + 2);
         }
-        __syncwarp();
-        TRACE(10)
-        act = r ? 0 : 1;
       }
-      if (act == 1) {
-        __threadfence_block();
-        TRACE(4)
-        propose_unit(sp, T, u, step, sm.lp_empty, sm.rows_eval);
-        TRACE(5)
-      } else if (act == 2) {
-        if (lane == 0) T.defer[atomicAdd(&sm.n_defer, 1)] = u;
-      }
+      __syncwarp();
+      if (!(ld_vol(&sm.res_flag) && t == ld_vol(&sm.res_step) + 1)) { ++t; continue; }
+      what = 3;  // this list was the drain pass of a resampling step
     }
-    TRACE(6)
+    // ---- what == 3: resampling after step sm.res_step; every warp of the CTA comes here
     __syncthreads();
-    PHASE_MARK(1)
-    // ------------------------------------------------------------------ previous step resolved?
-    if (step > 0 && sm.res_step < step - 1) {
-      if (warp == 0) {
-        if (lane == 0 && !bar_wait(bar, ep_prev, sp.err)) sm.fail = 1;
-        __syncwarp();
-        PHASE_MARK(4)
-        TRACE(9)
-        double mxv;
-        const bool r = resolve_weights(sp, step - 1, lw, cta, &mxv);
-        if (lane == 0) {
-          sm.res_mx = mxv;
-          sm.res_flag = r ? 1 : 0;
-          sm.res_claim = step - 1;
-          sm.res_step = step - 1;
-        }
-        TRACE(10)
-      }
-      __syncthreads();
-      if (sm.fail) return;
-      PHASE_MARK(5)
-    }
-    if (sm.res_flag) {
-      // resampling after step-1: this step's first pass applied every pending add; its predictive
-      // sums are discarded and the step is redone on the moved particles
-      if (!do_resample(sp, T, nu, step - 1, ev, epoch, sm.res_mx, lw, s_tmp, &sm.fail)) return;
-      if (tid == 0) sm.res_flag = 0;
-      PHASE_MARK(6)
-      first_pass = false;
-      goto redo_step;
-    }
-    // ------------------------------------------------------------------ deferred proposals, arrive
-    {
-      const int nd = sm.n_defer;
-      for (int i = warp; i < nd; i += NW) {
-        TRACE(4)
-        propose_unit(sp, T, T.defer[i], step, sm.lp_empty, sm.rows_eval);
-        TRACE(5)
-      }
-      for (int u = warp; u < nu; u += NW)  // units with no occupied row at all
-        if (T.foff[u + 1] == T.foff[u] && T.poff[u + 1] == T.poff[u])
-          propose_unit(sp, T, u, step, sm.lp_empty, sm.rows_eval);
-    }
+    const int st = sm.res_step;
+    if (!do_resample(sp, T, sm, nu, ns, st, s_tmp)) return;
+    init_queues(sp, T, sm, nu, ns, st + 1);
+    if (tid == 0) sm.res_flag = 0;
     __syncthreads();
-    epoch += G;
-    ep_prev = epoch;
-    if (tid == 0) {
-      __threadfence();
-      atomicAdd(bar, 1ull);
-    }
-    PHASE_MARK(2)
-    TRACE(7)
+    if (sm.fail) return;
+    t = st + 1;
+    PHASE_MARK(6)
   }
   // ------------------------------------------------------------------ weights of the last step
+  __syncthreads();
   {
-    const int st = sp.steps - 1;
+    const int st = steps - 1;
     if (warp == 0) {
-      if (lane == 0 && !bar_wait(bar, ep_prev, sp.err)) sm.fail = 1;
+      if (lane == 0 && !bar_wait((const unsigned long long*)sp.bar, sm.q[st & 1].ep, sp.err)) sm.fail = 1;
       __syncwarp();
-      double mxv;
-      const bool r = resolve_weights(sp, st, lw, cta, &mxv);
-      if (lane == 0) { sm.res_mx = mxv; sm.res_flag = r ? 1 : 0; }
+      if (sm.res_step < st) {
+        double mxv;
+        const bool r = resolve_ess(sp, st, &mxv);
+        if (lane == 0) { sm.res_mx = mxv; sm.res_flag = r ? 1 : 0; sm.res_step = st; }
+      }
     }
     __syncthreads();
     if (sm.fail) return;
-    PHASE_MARK(4)
     if (sm.res_flag) {
-      flush_adds(sp, T, nu, xbuf[st % 3], lf);
-      if (!do_resample(sp, T, nu, st, ev, epoch, sm.res_mx, lw, s_tmp, &sm.fail)) return;
-      PHASE_MARK(6)
+      flush_adds(sp, T, nu, xring + (size_t)(st % PMDI_OBS_RING) * sp.sm_x_bytes, lf);
+      if (!do_resample(sp, T, sm, nu, ns, st, s_tmp)) return;
     }
   }
   __syncthreads();
   if (tid < K) atomicAdd(sp.rows_eval + tid, (unsigned long long)sm.rows_eval[tid]);
-  if (cta == 0)
-    for (int p = tid; p < P; p += PMDI_NT) sp.lw_out[p] = __ldcg(lw + p);
-  if (timing)
-    for (int i = 0; i < 8; ++i) sp.phase_ns[(size_t)cta * 8 + i] = sm.tacc[i];
-  if (cta == 0 && tid == 0) sp.counters[2] = ev;
+  for (int sl = tid; sl < ns; sl += PMDI_NT) sp.lw_out[T.ulog[sl * K]] = T.lw_s[sl];
+  if (timing && tid < 8) sp.phase_ns[(size_t)cta * 8 + tid] = sm.tacc[tid] / NW;
+  if (cta == 0 && tid == 0) sp.counters[2] = sm.ev;
 #undef PHASE_MARK
 #undef TRACE
 }
