@@ -17,7 +17,7 @@ for it in range(3):
 ev = [l.split() for l in open(os.environ["PMDI_TRACE_FILE"])]
 ev = [(int(a), int(b), int(c)) for a, b, c in ev]
 t0 = min(c for _, _, c in ev)
-names = {30: "p_rc", 31: "p_max", 32: "p_cum", 33: "p_log", 34: "p_lab", 9: "res_start", 10: "res_end", 20: "E", 21: "ld0", 22: "prod", 23: "log", 24: "red", 29: "X", 1: "step_top", 2: "queue_start", 3: "item_done", 4: "prop_start", 5: "prop_end", 6: "queue_end", 7: "after_barrier", 8: "after_ess"}
+names = {30: "p_rc", 31: "p_max", 32: "p_cum", 33: "p_log", 34: "p_lab", 9: "res_start", 10: "res_end", 20: "E", 21: "ld0", 22: "prod", 23: "log", 24: "red", 29: "X", 1: "step_top", 2: "queue_start", 3: "item_done", 4: "prop_start", 5: "prop_end", 6: "leave_list", 7: "cta_arrive", 8: "after_ess"}
 for w in range(16):
     row = [(tag, c - t0) for ww, tag, c in ev if ww == w]
     out = []
