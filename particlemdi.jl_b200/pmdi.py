@@ -1,0 +1,335 @@
+"""Host side of ``pmdi()`` above the C-ABI: same entry point, asserts and CSV layout as the
+reference (src/pmdi.jl:36-390); the allocation sweep (:188-350, :373) and feature selection
+(:120-128, :354-370) run on the GPU through ``libpmdi_cuda.so``; the hyper-parameter updates
+(src/update_hypers.jl), ``align_labels!`` (src/misc.jl:61-96) and the CSV writer stay on the host,
+as the north-star prescribes.
+
+The reference is Julia; Julia is not installed here, so this mirror is Python and
+none of it has been compared with a Julia run.  Deviations from the literal reference, all
+switchable:
+
+* ``stale_gamma_table`` (default False).  The reference builds its table of log gamma over the
+  N^K label combinations once, before the loop (src/pmdi.jl:81-84), and never refreshes it, so
+  ``update_gamma!``, ``update_Phi!`` and ``update_Z`` (:178-185) keep using the INITIAL gamma.
+  Here the table follows gamma unless this flag is set.
+* ``sstar_compat`` (default False).  ``pmdi()`` does not permute the stored trajectories on
+  resampling (src/pmdi.jl:321-324); the tested twin ``__pmdi`` does (src/__pmdi.jl:285).
+* Random numbers: numpy ``Generator(seed)`` on the host, Philox addressed by ``(seed, iteration)``
+  on the device - not Julia's global RNG.
+
+There is no CPU fallback: without the CUDA library or a device this raises.
+"""
+from __future__ import annotations
+
+import math
+import time
+
+import numpy as np
+from scipy import special, stats
+
+from . import capi
+
+GAUSSIAN, CATEGORICAL, NEGBINOM = capi.GAUSSIAN, capi.CATEGORICAL, capi.NEGBINOM
+EPS = float(np.finfo(np.float64).eps)
+MAX_TABLE_ROWS = 50_000_000  # N^K rows of the hyper-parameter tables
+
+
+class GaussianCluster:      # names of the reference's cluster types (src/ParticleMDI.jl:31-36)
+    tag = GAUSSIAN
+
+
+class CategoricalCluster:
+    tag = CATEGORICAL
+
+
+class NegBinomCluster:
+    tag = NEGBINOM
+
+
+def _tag(t):
+    if isinstance(t, (int, np.integer)):
+        return int(t)
+    if hasattr(t, "tag"):
+        return int(t.tag)
+    raise TypeError(f"unknown cluster type {t!r}: only the three built-in types have device code")
+
+
+def phi_lab(K):
+    """calculate_Phi_lab (src/misc.jl:1-13): pairs (k1 < k2), row-major, 0-based here."""
+    return [(k1, k2) for k1 in range(K - 1) for k2 in range(k1 + 1, K)]
+
+
+# ------------------------------------------------------------------ hyper-parameter tables
+class HyperTables:
+    """c_combn, Gamma_c, Phi_index of src/pmdi.jl:69-92 (N^K rows)."""
+
+    def __init__(self, N, K):
+        rows = N ** K
+        if rows > MAX_TABLE_ROWS:
+            raise MemoryError(
+                f"the reference's hyper-parameter updates enumerate N^K = {N}^{K} = {rows:.3g} label "
+                "combinations (src/pmdi.jl:69-92); that is not feasible (SURVEY.md F6)")
+        self.N, self.K = N, K
+        idx = np.arange(rows)
+        # c_combn[:, K-k+1] = div(0:N^K-1, N^(K-k)) % N + 1 for k = 1..K (src/pmdi.jl:70-72):
+        # column j (0-based) cycles with period N^(j+1)
+        self.combn = np.stack([(idx // N ** j) % N for j in range(K)], axis=1)  # 0-based labels
+        pairs = phi_lab(K)
+        self.phi_index = (np.stack([self.combn[:, a] == self.combn[:, b] for a, b in pairs], axis=1)
+                          if K > 1 else np.ones((rows, 1), dtype=bool))
+        self.log_gamma_sum = None
+
+    def refresh(self, gamma):
+        """sum(Gamma_c, dims=2): sum_k log gamma[c_k, k] per combination."""
+        lg = np.log(gamma)
+        self.log_gamma_sum = sum(lg[self.combn[:, k], k] for k in range(self.K))
+
+    def norm_terms(self, phi):
+        """exp(Phi_index * log(1+Phi) + sum Gamma) per combination (update_hypers.jl:32,75-78,101-104)."""
+        if self.K > 1:
+            t = self.phi_index @ np.log(np.asarray(phi) + 1.0) + self.log_gamma_sum
+        else:
+            # K == 1: Phi = zeros(1) (src/pmdi.jl:61) and Phi_index is all ones -> adds log(1) = 0
+            t = self.log_gamma_sum.copy()
+        return np.exp(t)
+
+
+def update_Z(phi, tables):
+    """update_Z (src/update_hypers.jl:29-39)."""
+    return float(tables.norm_terms(phi).sum())
+
+
+def update_v(n_obs, Z, rng):
+    """update_v (src/update_hypers.jl:1-3): Gamma(n_obs, 1/Z)."""
+    return float(rng.gamma(n_obs, 1.0 / Z))
+
+
+def update_M(M, gamma, K, N, rng):
+    """update_M! (src/update_hypers.jl:5-26): random-walk Metropolis on each mass parameter,
+    prior Gamma(2, 0.25)."""
+    for k in range(K):
+        g, cur = gamma[:, k], M[k]
+        ll = stats.gamma.logpdf(g, a=cur / N, scale=1.0).sum() + stats.gamma.logpdf(cur, a=2.0, scale=0.25)
+        prop = cur + rng.normal() / 10.0
+        if prop <= 0.0:
+            alpha = 0.0
+        else:
+            ll_new = (stats.gamma.logpdf(g, a=prop / N, scale=1.0).sum()
+                      + stats.gamma.logpdf(prop, a=2.0, scale=0.25))
+            alpha = math.exp(min(ll_new - ll, 50.0))
+        if rng.random() < alpha:
+            M[k] = prop
+
+
+def update_gamma(gamma, phi, v, M, s, tables, rng):
+    """update_gamma! (src/update_hypers.jl:64-92): Gibbs update of every component weight, with the
+    normalising terms kept in step with the new value."""
+    N, K = tables.N, tables.K
+    norm = tables.norm_terms(phi)
+    for k in range(K):
+        counts = np.bincount(s[:, k] - 1, minlength=N)  # countn(s[:, k], n), :72
+        col = tables.combn[:, k]
+        for n in range(N):
+            rows = col == n
+            old = gamma[n, k]
+            beta_star = 1.0 + v * norm[rows].sum() / old
+            gamma[n, k] = rng.gamma(M[k] / N + counts[n], 1.0 / beta_star) + EPS
+            norm[rows] *= gamma[n, k] / old
+
+
+def update_phi(phi, v, s, tables, rng):
+    """update_Phi! (src/update_hypers.jl:95-128): each Phi is drawn from a mixture of Gammas indexed
+    by 0..n_agree, prior shape 1 and rate 5.  The weight of component j is restated literally from
+    :118-120, including ``- j * log(1 / beta_star)``."""
+    K = tables.K
+    norm = tables.norm_terms(phi)
+    for i, (a, b) in enumerate(phi_lab(K)):
+        cur = phi[i]
+        n_agree = int((s[:, a] == s[:, b]).sum())
+        rows = tables.phi_index[:, i]
+        beta_star = 5.0 + v * norm[rows].sum() / (1.0 + cur)
+        j = np.arange(n_agree + 1)
+        w = special.gammaln(j + 1.0) + stats.binom.logpmf(j, n_agree, 0.5) - j * math.log(1.0 / beta_star)
+        w = np.exp(w - w.max())
+        alpha_star = 1.0 + rng.choice(n_agree + 1, p=w / w.sum())
+        phi[i] = rng.gamma(alpha_star, 1.0 / beta_star)
+        norm[rows] *= (1.0 + phi[i]) / (1.0 + cur)
+
+
+def align_labels(s, phi, gamma, N, K, rng):
+    """align_labels! (src/misc.jl:61-96): Metropolis label swaps within each dataset that favour
+    agreement with the other datasets; gamma rows are swapped along with the labels."""
+    if K == 1:
+        return
+    pairs = phi_lab(K)
+    phi_log = np.log(np.asarray(phi) + 1.0)
+    for k in range(K):
+        others = [j for j in range(K) if j != k]
+        rel = np.array([phi_log[i] for i, (a, b) in enumerate(pairs) if a == k or b == k])
+        # pairs containing k, in pair order, line up with the other datasets in index order
+
+        def agree(rows, lab):  # count_equals (:98-108) dotted with the relevant log(1+Phi)
+            return float(((s[np.ix_(rows, others)] == lab).sum(axis=0) * rel).sum())
+
+        for label in list(dict.fromkeys(s[:, k].tolist())):  # unique(), first-appearance order
+            rows_l = np.flatnonzero(s[:, k] == label)
+            if rows_l.size == 0:
+                continue
+            for new_label in range(1, N + 1):
+                if new_label == label:
+                    continue
+                rows_n = np.flatnonzero(s[:, k] == new_label)
+                keep = agree(rows_l, label) + agree(rows_n, new_label)
+                swap = agree(rows_l, new_label) + agree(rows_n, label)
+                if rng.random() < math.exp(min(swap - keep, 50.0)):
+                    s[rows_l, k] = new_label
+                    s[rows_n, k] = label
+                    gamma[[new_label - 1, label - 1], k] = gamma[[label - 1, new_label - 1], k]
+                    label = new_label
+                    rows_l = np.flatnonzero(s[:, k] == label)
+
+
+# ------------------------------------------------------------------ CSV (src/pmdi.jl:147-158,377-383)
+def _jl(x):
+    """A Float64 as Julia's writedlm prints it (shortest round-trip form; exponents as 1.0e-5)."""
+    r = repr(float(x))
+    if "e" in r:
+        m, e = r.split("e")
+        if "." not in m:
+            m += ".0"
+        r = f"{m}e{int(e)}"
+    return r
+
+
+def csv_header(K, n_obs, dataNames):
+    pairs = phi_lab(K)
+    cols = [f"MassParameter_{k + 1}" for k in range(K)]
+    cols += [f"phi_{a + 1}_{b + 1}" for a, b in pairs] if K > 1 else ["phi_1_1"]
+    cols += ["ll"]
+    cols += [f"{dataNames[k]}_n{i + 1}" for k in range(K) for i in range(n_obs)]
+    return ",".join(cols)
+
+
+def csv_row(M, phi, ll, s):
+    """[M; Phi; ll; vec(s)] promoted to Float64 (labels print as ``3.0``), dataset-major."""
+    vals = [_jl(v) for v in M] + [_jl(v) for v in phi] + [_jl(ll)]
+    vals += [f"{int(v)}.0" for v in np.asarray(s).reshape(-1, order="F")]
+    return ",".join(vals)
+
+
+def n_hyper_columns(K):
+    """Columns before the allocations: K + C(K,2) + (K == 1) + 1 (consensus_map.jl:38)."""
+    return K + K * (K - 1) // 2 + (1 if K == 1 else 0) + 1
+
+
+def read_allocations(outputFile, K, n_obs, burnin=0, thin=1):
+    """Allocations of the retained rows, shape (rows, n_obs, K) - what ``generate_psm`` reads
+    (src/output_analysis/consensus_map.jl:31-48)."""
+    raw = np.loadtxt(outputFile, delimiter=",", skiprows=1, ndmin=2)
+    raw = raw[burnin::thin, n_hyper_columns(K):]
+    return raw.reshape(raw.shape[0], K, n_obs).transpose(0, 2, 1).astype(np.int64)
+
+
+def posterior_similarity(alloc):
+    """PSM per dataset (consensus_map.jl:50-56): fraction of retained rows in which two
+    observations share a label.  Returns (K, n, n)."""
+    rows, n, K = alloc.shape
+    out = np.zeros((K, n, n))
+    for k in range(K):
+        a = alloc[:, :, k]
+        for r in range(rows):
+            out[k] += a[r][:, None] == a[r][None, :]
+    return out / rows
+
+
+# ------------------------------------------------------------------ the entry point
+def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, featureSelect=None,
+         dataNames=None, seed=0, device=0, stale_gamma_table=False, sstar_compat=False):
+    """``pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile; thin, featureSelect,
+    dataNames)`` of src/pmdi.jl:36-40.  Side effect: the CSV file(s); returns a small dict of
+    timings and counters (the reference returns nothing)."""
+    K = len(dataFiles)
+    n_obs = int(dataFiles[0].shape[0])
+    if dataNames is None:
+        dataNames = [f"K{i + 1}" for i in range(K)]
+    # the reference's asserts (src/pmdi.jl:50-55)
+    assert len(dataTypes) == K, "Number of datatypes not equal to number of datasets"
+    assert len(dataNames) == K, "Number of data names not equal to number of datasets"
+    assert all(d.shape[0] == n_obs for d in dataFiles), \
+        "Datasets don't have same number of observations. Each row must correspond to the same " \
+        "underlying observational unit across datasets."
+    assert 0 < rho < 1, "ρ must be between 0 and 1"
+    assert 1 < N <= n_obs, \
+        f"Number of clusters must be greater than 1 and not greater than the number of observations, " \
+        f"suggest using floor(log(n)) = {int(math.floor(math.log(n_obs)))}"
+    assert particles > 1, "Conditional particle filter requires 2 or more particles"
+    n1 = int(math.floor(rho * n_obs))
+    assert n1 >= 1, "floor(ρ * n_obs) must be at least 1 (order_obs[n1:n_obs], src/pmdi.jl:209)"
+
+    types = [_tag(t) for t in dataTypes]
+    rng = np.random.default_rng(seed)
+    npairs = K * (K - 1) // 2
+    M = np.full(K, 2.0)                                           # :59
+    gamma = rng.gamma(1.0 / N, 1.0, (N, K)) + EPS                 # :60
+    phi = rng.gamma(1.0, 0.2, npairs) if K > 1 else np.zeros(1)   # :61
+    s = np.stack([1 + rng.choice(N, size=n_obs, p=gamma[:, k] / gamma[:, k].sum())
+                  for k in range(K)], axis=1).astype(np.int64)    # :63-66
+    tables = HyperTables(N, K)                                    # :69-92
+    tables.refresh(gamma)
+    Z = update_Z(phi, tables)                                     # :95
+    v = update_v(n_obs, Z, rng)                                   # :96
+
+    ctx = capi.Context(dataFiles, types, N, particles, device=device)  # raises without a GPU
+    stats_out = dict(sweep_device_ms=0.0, n_resamples=0, iterations=0)
+    ffile = None
+    try:
+        feature_null = None
+        if featureSelect is not None:                             # :106-128
+            flags = [rng.random(d.shape[1]) < 0.5 for d in dataFiles]
+            names = [f"{dataNames[k]}_d{d + 1}" for k in range(K) for d in range(dataFiles[k].shape[1])]
+            ffile = open(featureSelect, "w")
+            ffile.write(",".join(names) + "\n")
+            ffile.write(",".join("true" if f else "false" for fl in flags for f in fl) + "\n")
+            for k in range(K):
+                ctx.set_flags(k, flags[k].astype(np.uint8))
+            feature_null = [ctx.feature_null(k) for k in range(K)]
+        with open(outputFile, "w") as out:
+            out.write(csv_header(K, n_obs, dataNames) + "\n")     # :147-154
+            t0 = time.perf_counter()
+            out.write(csv_row(M, phi, 0, s) + "\n")               # :158
+            for it in range(1, iter + 1):                         # :164
+                order_obs = rng.permutation(n_obs) + 1            # :172
+                update_M(M, gamma, K, N, rng)                     # :176
+                if not stale_gamma_table:
+                    tables.refresh(gamma)
+                update_gamma(gamma, phi, v, M, s, tables, rng)    # :177
+                Pi = gamma / gamma.sum(axis=0, keepdims=True)     # :179
+                if not stale_gamma_table:
+                    tables.refresh(gamma)
+                if K > 1:
+                    update_phi(phi, v, s, tables, rng)            # :181-183
+                Z = update_Z(phi, tables)                         # :184
+                v = update_v(n_obs, Z, rng)                       # :185
+                r = ctx.sweep(s, order_obs, n1, Pi, phi if K > 1 else None,
+                              logweight_init=0.0 if it == 1 else 1.0,   # :99, :372
+                              seed=seed, it=it, sstar_compat=sstar_compat)  # :188-350, :373
+                s = np.array(r["s"], dtype=np.int64, order="C")
+                stats_out["sweep_device_ms"] += r["device_ms"]
+                stats_out["n_resamples"] += r["n_resamples"]
+                if featureSelect is not None:                     # :354-370
+                    for k in range(K):
+                        _, fl = ctx.feature_select(k, s[:, k], feature_null[k], seed=seed, it=it)
+                        flags[k] = fl.astype(bool)
+                        ctx.set_flags(k, fl)
+                align_labels(s, phi, gamma, N, K, rng)            # :375
+                ll = time.perf_counter() - t0                     # :377 (cumulative seconds)
+                if it % thin == 0:                                # :378-383
+                    out.write(csv_row(M, phi, ll, s) + "\n")
+                    if ffile is not None:
+                        ffile.write(",".join("true" if f else "false" for fl in flags for f in fl) + "\n")
+                stats_out["iterations"] = it
+    finally:
+        ctx.close()
+        if ffile is not None:
+            ffile.close()
+    return stats_out
