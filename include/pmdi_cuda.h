@@ -53,6 +53,24 @@ int pmdi_ctx_create(pmdi_ctx** out, int32_t K, int64_t n_obs, int32_t N, int32_t
                     int32_t device);
 int pmdi_ctx_destroy(pmdi_ctx* ctx);
 
+/*
+ * Particle sharding over the GPUs of one node: one context per GPU / process.
+ * Every rank binds the SAME datasets and is created with the GLOBAL particle count; rank r holds
+ * particles' statistics for P / n_ranks slots.  Per observation the ranks exchange their ESS
+ * partials, log-weights and allocations with NVLink peer stores from inside the sweep kernel, and
+ * resampled ancestors held by another rank are pulled through peer memory - no host round trip.
+ *   pmdi_ctx_set_ranks   before the first sweep (after pmdi_ctx_create);
+ *   pmdi_ipc_export      after all datasets are bound: the CUDA IPC handle of this rank's arena;
+ *   pmdi_ipc_import      all ranks' handles, in rank order (exchange them with any host mechanism).
+ * Every rank then calls pmdi_sweep_upload, a host barrier over all ranks, pmdi_sweep_run,
+ * pmdi_sweep_download, with identical arguments; every rank returns the same allocations.
+ */
+#define PMDI_IPC_HANDLE_BYTES 64
+int pmdi_ctx_set_ranks(pmdi_ctx* ctx, int32_t rank, int32_t n_ranks);
+int pmdi_ipc_export(pmdi_ctx* ctx, void* handle_out /* PMDI_IPC_HANDLE_BYTES */, int64_t* arena_bytes);
+int pmdi_ipc_import(pmdi_ctx* ctx, const void* handles /* n_ranks x PMDI_IPC_HANDLE_BYTES */,
+                    const int64_t* arena_bytes /* n_ranks, may be NULL */);
+
 /* Use an externally owned cudaStream_t (e.g. the host framework's current stream). */
 int pmdi_ctx_set_stream(pmdi_ctx* ctx, void* cuda_stream);
 void* pmdi_ctx_get_stream(pmdi_ctx* ctx);
@@ -93,7 +111,8 @@ typedef struct pmdi_sweep_out {
   int64_t* p_star;        /* 1-based selected particle (src/pmdi.jl:350)                      */
   double*  logweight;     /* P log-weights before the final reset (src/pmdi.jl:345), may be NULL */
   int64_t  n_resamples;   /* resampling events in this sweep                                  */
-  int64_t  n_copies;      /* particle stat blocks moved by resampling                         */
+  int64_t  n_copies;      /* particle stat blocks moved by resampling (all ranks)             */
+  int64_t  n_remote_rows; /* cluster rows this rank pulled from another rank's GPU (NVLink)   */
   int64_t  n_evals;       /* particle*cluster*feature predictive terms actually evaluated (occupied
                              clusters only; every empty label shares one evaluation per step) */
   int64_t  n_evals_dense; /* steps * P * N * sum_k D_k: the dense count of SURVEY.md 8(d)      */
@@ -109,7 +128,8 @@ typedef struct pmdi_sweep_out {
   double*  dbg_lw;        /* [steps][P] after coupling, before resampling                     */
   int32_t* dbg_alloc;     /* [steps][K][P] 1-based                                            */
   int32_t* dbg_anc;       /* [steps][P] 1-based ancestors, 0 when the step did not resample   */
-  int64_t* cluster_n;     /* [K][P][N] occupancy of every particle's clusters after the sweep */
+  int64_t* cluster_n;     /* [K][P][N] occupancy of every particle's clusters after the sweep
+                             (-1 for particles held by another rank) */
 } pmdi_sweep_out;
 
 /*

@@ -27,7 +27,9 @@ EXPORTS = [
     "pmdi_ctx_set_stream", "pmdi_ctx_get_stream", "pmdi_set_dataset", "pmdi_set_feature_flags",
     "pmdi_sweep", "pmdi_sweep_upload", "pmdi_sweep_run", "pmdi_sweep_download",
     "pmdi_feature_null", "pmdi_feature_select", "pmdi_cluster_eval", "pmdi_uniform",
+    "pmdi_ctx_set_ranks", "pmdi_ipc_export", "pmdi_ipc_import",
 ]
+IPC_HANDLE_BYTES = 64
 
 
 def build(force: bool = False) -> str:
@@ -54,7 +56,7 @@ class SweepArgs(C.Structure):
 class SweepOut(C.Structure):
     _fields_ = [
         ("s", C.c_void_p), ("p_star", C.c_void_p), ("logweight", C.c_void_p),
-        ("n_resamples", C.c_int64), ("n_copies", C.c_int64), ("n_evals", C.c_int64),
+        ("n_resamples", C.c_int64), ("n_copies", C.c_int64), ("n_remote_rows", C.c_int64), ("n_evals", C.c_int64),
         ("n_evals_dense", C.c_int64), ("rows_evaluated", C.c_int64 * 8),
         ("device_ms", C.c_double), ("sweep_kernel_ms", C.c_double), ("phase_ms", C.c_double * 8),
         ("phase_ms_max", C.c_double * 8),
@@ -94,6 +96,9 @@ def lib():
                                           C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.pmdi_cluster_eval.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_int64, C.c_int64,
                                         C.c_void_p, C.c_void_p]
+        L.pmdi_ctx_set_ranks.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
+        L.pmdi_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.pmdi_ipc_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.pmdi_uniform.restype = C.c_double
         L.pmdi_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.c_uint32]
@@ -125,7 +130,11 @@ def uniform(seed, it, kind, step, k, index) -> float:
 class Context:
     """One sweep context: K datasets bound to one GPU (``pmdi_ctx``)."""
 
-    def __init__(self, data, types, N: int, particles: int, device: int = 0):
+    def __init__(self, data, types, N: int, particles: int, device: int = 0, rank: int = 0,
+                 n_ranks: int = 1):
+        """``particles`` is the GLOBAL count; with ``n_ranks > 1`` this rank holds particles / n_ranks
+        of them (call :meth:`connect` after construction)."""
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
         self.K = len(data)
         self.n = int(data[0].shape[0])
         self.N, self.P = int(N), int(particles)
@@ -134,6 +143,8 @@ class Context:
         h = C.c_void_p()
         _check(lib().pmdi_ctx_create(C.byref(h), self.K, self.n, self.N, self.P, device))
         self.h = h
+        if self.n_ranks > 1:
+            _check(lib().pmdi_ctx_set_ranks(self.h, self.rank, self.n_ranks))
         for k, (d, t) in enumerate(zip(data, types)):
             if d.shape[0] != self.n:
                 raise AssertionError("datasets must have the same number of rows")  # src/pmdi.jl:52
@@ -144,6 +155,43 @@ class Context:
                 a = np.asfortranarray(d, dtype=np.int64)
                 kind = I64
             _check(lib().pmdi_set_dataset(self.h, k, t, kind, _ptr(a), self.n, self.D[k], self.n))
+
+    # ---- particle sharding over the GPUs of one node ------------------------------------------
+    def export_handle(self):
+        """(IPC handle bytes, arena size) of this rank's shared arena."""
+        buf = (C.c_ubyte * IPC_HANDLE_BYTES)()
+        nbytes = C.c_int64(0)
+        _check(lib().pmdi_ipc_export(self.h, buf, C.byref(nbytes)))
+        return bytes(buf), int(nbytes.value)
+
+    def import_handles(self, handles, sizes=None):
+        blob = b"".join(handles)
+        assert len(blob) == self.n_ranks * IPC_HANDLE_BYTES
+        hb = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        sz = None if sizes is None else (C.c_int64 * self.n_ranks)(*sizes)
+        _check(lib().pmdi_ipc_import(self.h, hb, sz))
+
+    def connect(self, group=None):
+        """Exchange the arena handles over ``torch.distributed`` (plumbing only: the per-observation
+        exchange runs inside the sweep kernel over NVLink peer memory)."""
+        import torch.distributed as dist
+        self._group = group
+        mine = self.export_handle()
+        allh = [None] * self.n_ranks
+        dist.all_gather_object(allh, mine, group=group)
+        self.import_handles([h for h, _ in allh], [n for _, n in allh])
+        dist.barrier(group=group)
+
+    def sweep_sharded(self, *args, **kw):
+        """``sweep`` on every rank with identical arguments: upload, barrier over the ranks (every
+        rank's grid counter is reset before any kernel starts), run, download."""
+        import torch.distributed as dist
+        if kw.pop("sstar_compat", False):
+            raise NotImplementedError("sstar_compat is not offered through the split upload/run path")
+        self.upload(*args, **kw)
+        dist.barrier(group=getattr(self, "_group", None))
+        self.run()
+        return self.download()
 
     def close(self):
         if getattr(self, "h", None):
@@ -225,6 +273,7 @@ class Context:
         res["p_star"] = int(res["p_star"][0])
         res["n_resamples"] = int(o.n_resamples)
         res["n_copies"] = int(o.n_copies)
+        res["n_remote_rows"] = int(o.n_remote_rows)
         res["n_evals"] = int(o.n_evals)
         res["n_evals_dense"] = int(o.n_evals_dense)
         res["rows_evaluated"] = [int(v) for v in o.rows_evaluated]

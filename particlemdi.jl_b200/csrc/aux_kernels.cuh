@@ -32,9 +32,8 @@ __global__ void k_sweep_init(SweepParams sp) {
     sp.logical_of[sp.P + t] = t;
   }
   if (t == 0) {
-    *(unsigned long long*)sp.bar = 0ull;
     *sp.err = 0;
-    sp.counters[0] = sp.counters[1] = sp.counters[2] = 0;
+    sp.counters[0] = sp.counters[1] = sp.counters[2] = sp.counters[3] = 0;
     sp.plan_out[0] = 0;
     for (int k = 0; k < PMDI_MAX_K; ++k) sp.rows_eval[k] = 0ull;
   }
@@ -118,7 +117,7 @@ __global__ void k_prefix_build(SweepParams sp, const int* members, const int* of
   const DsDev& ds = sp.ds[k];
   if (q >= ds.Dp) return;
   const int b = off[k * (sp.N + 1) + m], e = off[k * (sp.N + 1) + m + 1];
-  const long long row = (long long)sp.P * sp.N + m;
+  const long long row = (long long)sp.Ps * sp.N + m;
   build_row_feature(ds, row, q, members + (size_t)k * (sp.n1 - 1) + b, e - b, 1);
   if (q == 0) ds.n[row] = e - b;
 }
@@ -127,7 +126,7 @@ __global__ void k_prefix_build(SweepParams sp, const int* members, const int* of
 __global__ void k_proto_aux(SweepParams sp) {
   const int k = blockIdx.y, m = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const DsDev& ds = sp.ds[k];
-  const long long row = (long long)sp.P * sp.N + m;
+  const long long row = (long long)sp.Ps * sp.N + m;
   const int n = ds.n[row];
   for (int j = w; j < ds.J; j += blockDim.x >> 5) {
     if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);
@@ -141,12 +140,12 @@ __global__ void k_broadcast(SweepParams sp) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long GW = ((long long)gridDim.x * blockDim.x) >> 5;
-  const long long total = (long long)sp.K * sp.P * sp.N;
+  const long long total = (long long)sp.K * sp.Ps * sp.N;
   for (long long idx = gw; idx < total; idx += GW) {
-    const int k = (int)(idx / ((long long)sp.P * sp.N));
-    const long long rem = idx - (long long)k * sp.P * sp.N;
+    const int k = (int)(idx / ((long long)sp.Ps * sp.N));
+    const long long rem = idx - (long long)k * sp.Ps * sp.N;
     const int m = (int)(rem % sp.N);
-    row_copy(sp.ds[k], (long long)sp.P * sp.N + m, rem, lane);
+    row_copy(sp.ds[k], 0, (long long)sp.Ps * sp.N + m, rem, lane);
   }
 }
 
@@ -197,7 +196,8 @@ __global__ void k_finish(SweepParams sp, int compat, long long* s_out, long long
       const int k = (int)(idx / ((size_t)P * N));
       const size_t rem = idx - (size_t)k * P * N;
       const int p = (int)(rem / N), m = (int)(rem % N);
-      cluster_n[idx] = sp.ds[k].n[(long long)slot[p] * N + m];
+      const int ls = slot[p] - sp.slot0;  // clusters of particles held by another rank: -1
+      cluster_n[idx] = (ls >= 0 && ls < sp.Ps) ? sp.ds[k].n[(long long)ls * N + m] : -1;
     }
   }
 }
@@ -280,7 +280,7 @@ __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
     for (int q = lane; q < ds.Dp; q += 32) ((int*)xs_raw)[q] = ds.flag[q] ? src[q] : skip;
   }
   __syncwarp();
-  const long long row = (long long)sp.P * sp.N;
+  const long long row = (long long)sp.Ps * sp.N;
   const int n = ds.n[row];
   double acc = ds.rc[n];
   for (int j = 0; j < ds.J; ++j) {
@@ -298,14 +298,14 @@ __global__ void k_build_one(SweepParams sp, int k, const int* members, int cnt) 
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const DsDev& ds = sp.ds[k];
   if (q >= ds.Dp) return;
-  const long long row = (long long)sp.P * sp.N;
+  const long long row = (long long)sp.Ps * sp.N;
   build_row_feature(ds, row, q, members, cnt, 1);
   if (q == 0) ds.n[row] = cnt;
 }
 __global__ void k_aux_one(SweepParams sp, int k) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const DsDev& ds = sp.ds[k];
-  const long long row = (long long)sp.P * sp.N;
+  const long long row = (long long)sp.Ps * sp.N;
   const int n = ds.n[row];
   for (int j = w; j < ds.J; j += blockDim.x >> 5) {
     if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);
@@ -331,7 +331,7 @@ __global__ void k_empty_lp(SweepParams sp, double* lp_empty) {
     for (int q = tid; q < words; q += blockDim.x) dst[q] = src[q];
   }
   __syncthreads();
-  const long long row = (long long)(sp.P + 1) * sp.N;
+  const long long row = (long long)(sp.Ps + 1) * sp.N;
   for (int it = warp; it < sp.K * sp.Jmax; it += NW) {
     const int k = it / sp.Jmax, j = it - k * sp.Jmax;
     const DsDev& ds = sp.ds[k];

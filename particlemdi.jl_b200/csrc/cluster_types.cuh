@@ -486,16 +486,19 @@ __device__ __forceinline__ double cat_eval_item(const DsDev& ds, long long row, 
 // Row movement for resampling (src/pmdi.jl:318-341 in dense form): one warp moves one cluster
 // row src -> dst, or resets dst to the empty state when the source label is empty.
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void row_copy(const DsDev& ds, long long src, long long dst, int lane) {
-  const int ns = ldcg_i32(ds.n + src), nd = ldcg_i32(ds.n + dst);
+__device__ __noinline__ void row_copy(const DsDev& ds, long long sdelta, long long src, long long dst, int lane) {
+  // sdelta: byte offset from this rank's arena to the arena of the rank that holds the source row
+  // (0 when it is local); the source is read through NVLink peer memory then.
+#define PMDI_SRC(ptr_) ((decltype(ptr_))((const char*)(ptr_) + sdelta))
+  const int ns = ldcg_i32(PMDI_SRC(ds.n) + src), nd = ldcg_i32(ds.n + dst);
   if (ns == 0 && nd == 0) return;
   const int Dp = ds.Dp;
   if (ds.type == T_GAUSSIAN) {
     for (int q = 2 * lane; q < Dp; q += 64) {
       double2 a, b, c, d;
       if (ns) {
-        a = ldcg_f64x2(ds.mu + src * Dp + q); b = ldcg_f64x2(ds.lamn + src * Dp + q);
-        c = ldcg_f64x2(ds.sum + src * Dp + q); d = ldcg_f64x2(ds.beta + src * Dp + q);
+        a = ldcg_f64x2(PMDI_SRC(ds.mu) + src * Dp + q); b = ldcg_f64x2(PMDI_SRC(ds.lamn) + src * Dp + q);
+        c = ldcg_f64x2(PMDI_SRC(ds.sum) + src * Dp + q); d = ldcg_f64x2(PMDI_SRC(ds.beta) + src * Dp + q);
       } else {
         a = make_double2(0.0, 0.0); b = make_double2(1.0, 1.0);
         c = make_double2(0.0, 0.0); d = make_double2(0.5, 0.5);
@@ -507,16 +510,17 @@ __device__ __noinline__ void row_copy(const DsDev& ds, long long src, long long 
     const long long W = (long long)ds.Lmax * Dp;
     for (long long q = 4 * lane; q < W; q += 128) {
       uint4 v = make_uint4(0, 0, 0, 0);
-      if (ns) v = __ldcg((const uint4*)(ds.cnt + src * W + q));
+      if (ns) v = __ldcg((const uint4*)(PMDI_SRC(ds.cnt) + src * W + q));
       *(uint4*)(ds.cnt + dst * W + q) = v;
     }
   } else {
     for (int q = 2 * lane; q < Dp; q += 64) {
       longlong2 v = make_longlong2(0, 0);
-      if (ns) v = ldcg_i64x2(ds.S + src * Dp + q);
+      if (ns) v = ldcg_i64x2(PMDI_SRC(ds.S) + src * Dp + q);
       *(longlong2*)(ds.S + dst * Dp + q) = v;
     }
   }
-  for (int j = lane; j < ds.J; j += 32) ds.aux[dst * ds.J + j] = ns ? ldcg_f64(ds.aux + src * ds.J + j) : 0.0;
+  for (int j = lane; j < ds.J; j += 32) ds.aux[dst * ds.J + j] = ns ? ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + j) : 0.0;
   if (lane == 0) ds.n[dst] = ns;
+#undef PMDI_SRC
 }

@@ -38,9 +38,15 @@ template <class T>
 struct DevBuf {
   T* p = nullptr;
   size_t cap = 0;
+  bool owned = true;
+  void view(void* ptr, size_t n) {  // a slice of the context's shared arena (not freed here)
+    if (p && owned) cudaFree(p);
+    p = (T*)ptr; cap = n; owned = false;
+  }
   cudaError_t ensure(size_t n) {
     if (n <= cap && p) return cudaSuccess;
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
+    owned = true;
     p = nullptr;
     cap = 0;
     cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(n, 1) * sizeof(T));
@@ -48,9 +54,10 @@ struct DevBuf {
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p && owned) cudaFree(p);
     p = nullptr;
     cap = 0;
+    owned = true;
   }
 };
 
@@ -86,6 +93,14 @@ struct pmdi_ctx {
   int n_sm = 0, G = 0;
   std::vector<Dataset> ds;
   bool layout_dirty = true;
+  // everything another rank has to reach (statistics, grid counter, ESS partials, log-weights, allocation
+  // log) lives in ONE allocation with the same layout on every rank: one IPC handle, peer address =
+  // local address + delta
+  unsigned char* arena = nullptr;
+  size_t arena_bytes = 0;
+  int rank = 0, R = 1, Ps = 0;  // this rank, ranks, particle slots held here (P / R)
+  long long peer_delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // static layout
   std::vector<int> cta_off, cta_units;
   int max_units = 0, sm_x_bytes = 0, lf_T = 0, lf_want = 0, item_cap = 0, Jmax = 0;
@@ -200,6 +215,62 @@ int build_layout(pmdi_ctx* c) {
     CK(c->lf_dev.ensure(c->lf_want));
     CK(cudaMemcpy(c->lf_dev.p, c->lf_host.data(), sizeof(double) * c->lf_want, cudaMemcpyHostToDevice));
   }
+  // ---- the shared arena: [grid counter | ESS partials | log-weights | allocation log | statistics]
+  if (c->P % c->R != 0) return fail(1, "pmdi: particles must be a multiple of the number of ranks");
+  c->Ps = c->P / c->R;
+  if (c->R > 1 && c->peer_base[c->rank] != nullptr)
+    return fail(1, "pmdi: datasets cannot be re-bound after pmdi_ipc_export (the peers hold this layout)");
+  const long long rows = (long long)(c->Ps + 2) * c->N;  // particle slots, prototypes, the shared empty row
+  const int Gmax = std::min(c->n_sm, c->Ps);
+  size_t off_b = 0;
+  auto take = [&](size_t bytes) { const size_t o = off_b; off_b = (off_b + bytes + 255) / 256 * 256; return o; };
+  const size_t o_bar = take(64);
+  const size_t o_ess = take(sizeof(double) * 6 * (size_t)c->R * Gmax);
+  const size_t o_lw = take(sizeof(double) * (size_t)c->P);
+  const size_t o_log = take((size_t)c->n * K * c->P);  // at most n_obs observation steps
+  struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n; };
+  std::vector<Off> offs(K);
+  for (int k = 0; k < K; ++k) {
+    Dataset& s = c->ds[k];
+    Off& o = offs[k];
+    std::memset(&o, 0, sizeof(o));
+    if (s.type == T_GAUSSIAN) {
+      o.mu = take(8 * rows * s.Dp); o.lamn = take(8 * rows * s.Dp);
+      o.sum = take(8 * rows * s.Dp); o.beta = take(8 * rows * s.Dp);
+    } else if (s.type == T_CATEGORICAL) {
+      o.cnt = take(4 * rows * (size_t)s.Lmax * s.Dp);
+    } else {
+      o.S = take(8 * rows * s.Dp);
+    }
+    o.part = take(8 * rows * s.J); o.aux = take(8 * rows * s.J); o.n = take(4 * rows);
+  }
+  if (c->arena) { cudaFree(c->arena); c->arena = nullptr; }
+  CK(cudaMalloc((void**)&c->arena, off_b));
+  CK(cudaMemset(c->arena, 0, off_b));
+  c->arena_bytes = off_b;
+  unsigned char* A = c->arena;
+  c->bar.view(A + o_bar, 16);
+  c->ess_part.view(A + o_ess, 6 * (size_t)c->R * Gmax);
+  c->lw.view(A + o_lw, c->P);
+  c->alloc_log.view(A + o_log, (size_t)c->n * K * c->P);
+  for (int k = 0; k < K; ++k) {
+    Dataset& s = c->ds[k];
+    const Off& o = offs[k];
+    if (s.type == T_GAUSSIAN) {
+      s.mu.view(A + o.mu, rows * s.Dp); s.lamn.view(A + o.lamn, rows * s.Dp);
+      s.sum.view(A + o.sum, rows * s.Dp); s.beta.view(A + o.beta, rows * s.Dp);
+    } else if (s.type == T_CATEGORICAL) {
+      s.cnt.view(A + o.cnt, rows * (size_t)s.Lmax * s.Dp);
+    } else {
+      s.S.view(A + o.S, rows * s.Dp);
+    }
+    s.part.view(A + o.part, rows * s.J); s.aux.view(A + o.aux, rows * s.J); s.n.view(A + o.n, rows);
+    DsDev d;
+    fill_dsdev(c, k, d);
+    k_init_rows<<<c->n_sm * 4, 256, 0, c->stream>>>(d, rows);
+    CK(cudaGetLastError());
+  }
+  CK(cudaStreamSynchronize(c->stream));
   c->layout_dirty = false;
   c->assigned = false;
   return 0;
@@ -209,7 +280,7 @@ int build_layout(pmdi_ctx* c) {
 // CTA-local), round-robin so that the counts differ by at most one; then the shared-memory
 // budget of the sweep kernel.
 int assign_units(pmdi_ctx* c) {
-  const int K = c->K, P = c->P, N = c->N;
+  const int K = c->K, P = c->Ps, N = c->N;  // the particle slots this rank holds
   c->G = std::min(c->n_sm, P);  // one persistent CTA per SM; never a CTA without a particle
   const int G = c->G;
   c->cta_off.assign(G + 1, 0);
@@ -263,6 +334,8 @@ int fill_params(pmdi_ctx* c) {
     off += c->ds[k].Dp * (c->ds[k].type == T_GAUSSIAN ? 8 : 4);
   }
   sp.K = c->K; sp.N = c->N; sp.P = c->P; sp.n_obs = (int)c->n; sp.G = c->G;
+  sp.R = c->R; sp.rank = c->rank; sp.Ps = c->Ps; sp.slot0 = c->rank * c->Ps;
+  for (int r = 0; r < 8; ++r) sp.peer_delta[r] = c->peer_delta[r];
   sp.Jmax = c->Jmax;
   sp.cta_off = c->d_cta_off.p; sp.cta_units = c->d_cta_units.p;
   sp.max_units = c->max_units; sp.sm_x_bytes = c->sm_x_bytes; sp.lf_T = c->lf_T;
@@ -345,6 +418,9 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   for (auto* b : dl) b->release();
   c->lab.release(); c->alloc_log.release(); c->copies.release(); c->bar.release();
   c->rows_eval.release(); c->phase_ns.release(); c->scratch_u8.release();
+  for (int r = 0; r < c->R; ++r)
+    if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
+  if (c->arena) cudaFree(c->arena);
   if (c->ev0) { cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1); cudaEventDestroy(c->ev2); cudaEventDestroy(c->ev3); }
   if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -421,25 +497,53 @@ int pmdi_set_dataset(pmdi_ctx* c, int32_t k, int32_t type_tag, int32_t elem_kind
   }
   CK(s.d_flag.ensure(Dp));
   CK(cudaMemcpy(s.d_flag.p, s.flag.data(), Dp, cudaMemcpyHostToDevice));
-  const long long rows = (long long)(c->P + 2) * c->N;
-  if (type_tag == PMDI_GAUSSIAN) {
-    CK(s.mu.ensure(rows * Dp)); CK(s.lamn.ensure(rows * Dp));
-    CK(s.sum.ensure(rows * Dp)); CK(s.beta.ensure(rows * Dp));
-  } else if (type_tag == PMDI_CATEGORICAL) {
-    CK(s.cnt.ensure(rows * s.Lmax * Dp));
-  } else {
-    CK(s.S.ensure(rows * Dp));
-  }
-  CK(s.part.ensure(rows * s.J)); CK(s.aux.ensure(rows * s.J)); CK(s.n.ensure(rows));
   s.bound = true;
   s.rc_dirty = true;
-  c->layout_dirty = true;
-  DsDev d;
-  fill_dsdev(c, k, d);
-  k_init_rows<<<c->n_sm * 4, 256, 0, c->stream>>>(d, rows);
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(c->stream));
+  c->layout_dirty = true;  // the statistics are (re)allocated in the shared arena by build_layout()
   return 0;
+}
+
+int pmdi_ctx_set_ranks(pmdi_ctx* c, int32_t rank, int32_t n_ranks) {
+  if (!c) return fail(1, "NULL context");
+  if (n_ranks < 1 || n_ranks > 8 || rank < 0 || rank >= n_ranks) return fail(1, "pmdi_ctx_set_ranks: need 0 <= rank < n_ranks <= 8");
+  if (c->P % n_ranks != 0) return fail(1, "pmdi_ctx_set_ranks: particles must be a multiple of the number of ranks");
+  if (c->P / n_ranks < 1) return fail(1, "pmdi_ctx_set_ranks: fewer particles than ranks");
+  if (c->arena) return fail(1, "pmdi_ctx_set_ranks: call it before the first sweep / export");
+  c->rank = rank; c->R = n_ranks; c->Ps = c->P / n_ranks;
+  c->layout_dirty = true;
+  return 0;
+}
+
+static int prepare(pmdi_ctx* c);
+
+int pmdi_ipc_export(pmdi_ctx* c, void* handle_out, int64_t* arena_bytes) {
+  if (!c || !handle_out) return fail(1, "pmdi_ipc_export: NULL argument");
+  int rc = prepare(c);  // builds the shared arena (all datasets must be bound)
+  if (rc) return rc;
+  static_assert(sizeof(cudaIpcMemHandle_t) == PMDI_IPC_HANDLE_BYTES, "IPC handle size");
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, c->arena));
+  std::memcpy(handle_out, &h, sizeof(h));
+  if (arena_bytes) *arena_bytes = (int64_t)c->arena_bytes;
+  return 0;
+}
+
+int pmdi_ipc_import(pmdi_ctx* c, const void* handles, const int64_t* arena_bytes) {
+  if (!c || !handles) return fail(1, "pmdi_ipc_import: NULL argument");
+  if (!c->arena) return fail(1, "pmdi_ipc_import: call pmdi_ipc_export first");
+  CK(cudaSetDevice(c->device));
+  for (int r = 0; r < c->R; ++r) {
+    if (arena_bytes && arena_bytes[r] != (int64_t)c->arena_bytes)
+      return fail(1, "pmdi_ipc_import: rank " + std::to_string(r) + " has a different arena layout (same datasets, N, particles on every rank?)");
+    if (r == c->rank) { c->peer_base[r] = c->arena; c->peer_delta[r] = 0; continue; }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, (const unsigned char*)handles + (size_t)r * sizeof(h), sizeof(h));
+    void* p = nullptr;
+    CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_base[r] = p;
+    c->peer_delta[r] = (long long)((unsigned char*)p - c->arena);
+  }
+  return fill_params(c);
 }
 
 int pmdi_set_feature_flags(pmdi_ctx* c, int32_t k, const uint8_t* flags) {
@@ -456,6 +560,7 @@ int pmdi_set_feature_flags(pmdi_ctx* c, int32_t k, const uint8_t* flags) {
 
 static int prepare(pmdi_ctx* c) {
   CK(cudaSetDevice(c->device));
+  if (c->Ps == 0) c->Ps = c->P / c->R;
   if (c->layout_dirty) {
     int rc = build_layout(c);
     if (rc) return rc;
@@ -527,14 +632,14 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
     sp.tape_select = c->tape_select.p;
   }
   // state buffers
-  CK(c->lw.ensure(P)); CK(c->ess_part.ensure(6 * (size_t)c->G)); CK(c->lw_out.ensure(P)); CK(c->slot_of.ensure(2 * (size_t)P));
+  CK(c->lw_out.ensure(P)); CK(c->slot_of.ensure(2 * (size_t)P));
   CK(c->logical_of.ensure(2 * (size_t)P)); CK(c->inc.ensure(2 * (size_t)K * P)); CK(c->lp_empty.ensure((size_t)steps * K));
-  CK(c->lab.ensure(2 * (size_t)K * P)); CK(c->alloc_log.ensure((size_t)steps * K * P));
+  CK(c->lab.ensure(2 * (size_t)K * P));
   CK(c->anc_log.ensure((size_t)steps * P)); CK(c->ev_of_step.ensure(steps));
   CK(c->sc_w.ensure(P)); CK(c->sc_pp.ensure(P)); CK(c->sc_u.ensure(P));
   CK(c->sc_j.ensure(P)); CK(c->sc_anc0.ensure(P)); CK(c->sc_a.ensure(P)); CK(c->sc_b.ensure(P));
   CK(c->sc_c.ensure(P)); CK(c->sc_d.ensure(P)); CK(c->copies.ensure(P)); CK(c->plan_out.ensure(4));
-  CK(c->bar.ensure(4)); CK(c->err.ensure(4)); CK(c->rows_eval.ensure(PMDI_MAX_K)); CK(c->counters.ensure(4));
+  CK(c->err.ensure(4)); CK(c->rows_eval.ensure(PMDI_MAX_K)); CK(c->counters.ensure(4));
   CK(c->phase_ns.ensure(8 * (size_t)c->G)); CK(c->d_pstar.ensure(1)); CK(c->cluster_n.ensure((size_t)K * P * N));
   CK(c->members.ensure((size_t)K * std::max<long long>(a->n1 - 1, 1))); CK(c->mem_off.ensure((size_t)K * (N + 1)));
   CK(c->cur_at.ensure(steps));
@@ -554,8 +659,15 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
     CK(c->dbg_lp.ensure((size_t)steps * K * P * N)); CK(c->dbg_lw.ensure((size_t)steps * P));
     CK(c->dbg_alloc.ensure((size_t)steps * K * P)); CK(c->dbg_anc.ensure((size_t)steps * P));
     CK(cudaMemsetAsync(c->dbg_anc.p, 0, sizeof(int) * (size_t)steps * P, st));
+    // with several ranks each entry of these is written by the rank that holds the particle: zero the rest
+    CK(cudaMemsetAsync(c->dbg_lp.p, 0, sizeof(double) * (size_t)steps * K * P * N, st));
+    CK(cudaMemsetAsync(c->dbg_lw.p, 0, sizeof(double) * (size_t)steps * P, st));
+    CK(cudaMemsetAsync(c->dbg_alloc.p, 0, sizeof(int) * (size_t)steps * K * P, st));
     sp.dbg_lp = c->dbg_lp.p; sp.dbg_lw = c->dbg_lw.p; sp.dbg_alloc = c->dbg_alloc.p; sp.dbg_anc = c->dbg_anc.p;
   }
+  if (c->R > 1 && c->peer_base[c->rank] == nullptr)
+    return fail(1, "pmdi_sweep: call pmdi_ipc_export / pmdi_ipc_import on every rank first");
+  CK(cudaMemsetAsync(c->bar.p, 0, 16, st));  // with R > 1 the caller barriers all ranks between upload and run
   CK(cudaMemsetAsync(c->phase_ns.p, 0, 64 * (size_t)c->G, st));
   CK(c->wd_state.ensure((size_t)c->G * 16 * 16));
   CK(cudaMemsetAsync(c->wd_state.p, 0xff, sizeof(int) * (size_t)c->G * 16 * 16, st));
@@ -667,6 +779,7 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   if (o->p_star) *o->p_star = pstar;
   o->n_resamples = counters[0];
   o->n_copies = counters[1];
+  o->n_remote_rows = counters[3];
   long long ev = 0, dense = 0;
   for (int k = 0; k < K; ++k) {
     rows[k] += (unsigned long long)steps;  // the shared empty cluster: one evaluation per step

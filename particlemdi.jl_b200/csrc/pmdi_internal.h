@@ -9,9 +9,9 @@
  *   NegBinom     S[r][q]                                                         (i64)
  * plus per row: n[r] (cluster size), aux[r][j] (x-independent part of the predictive, per
  * 256-feature block j), part[r][j] (this step's predictive partial sums).
- * Slots 0..P-1 are particles (a logical->slot table follows resampling so that survivors are
- * never copied), slot P holds the rho-prefix prototypes, slot P+1 row 0 is the shared empty
- * cluster that stands for every label with n == 0.
+ * Local slots 0..Ps-1 are particles (a logical->slot table over the P GLOBAL slots follows
+ * resampling so that survivors are never copied), local slot Ps holds the rho-prefix prototypes,
+ * local slot Ps+1 row 0 is the shared empty cluster that stands for every label with n == 0.
  */
 #ifndef PMDI_INTERNAL_H
 #define PMDI_INTERNAL_H
@@ -44,6 +44,10 @@ struct DsDev {
 struct SweepParams {
   int K, N, P, n_obs, n1, steps;
   int G, flags;
+  /* particle sharding: R ranks (one GPU each), this one holds slots [slot0, slot0 + Ps) of the P global
+     slots; peer_delta[r] turns a pointer into this rank's shared arena into the same object on rank r */
+  int R, rank, Ps, slot0;
+  long long peer_delta[8];
   DsDev ds[PMDI_MAX_K];
   const double* Pi;      /* [K][N]                                          */
   const double* l1phi;   /* [npairs] log(1+phi)                             */

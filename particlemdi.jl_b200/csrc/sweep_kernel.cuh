@@ -223,6 +223,32 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
   asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+// the grid counter as seen by this rank: other GPUs add to it through NVLink when R > 1
+__device__ __forceinline__ unsigned long long ld_counter(const SweepParams& sp) {
+  const unsigned long long* bar = (const unsigned long long*)sp.bar;
+  return sp.R > 1 ? ld_acquire_sys_u64(bar) : ld_acquire_u64(bar);
+}
+// the same object in rank r's shared arena (r == own rank: the pointer itself)
+template <class T>
+__device__ __forceinline__ T* on_rank(const SweepParams& sp, T* p, int r) {
+  return (T*)((char*)p + sp.peer_delta[r]);
+}
+// release everything this thread has observed, then add one arrival to EVERY rank's counter
+__device__ __forceinline__ void arrive_all(const SweepParams& sp) {
+  if (sp.R > 1) {
+    __threadfence_system();
+#pragma unroll 1
+    for (int r = 0; r < sp.R; ++r) atomicAdd_system(on_rank(sp, (unsigned long long*)sp.bar, r), 1ull);
+  } else {
+    __threadfence();
+    atomicAdd((unsigned long long*)sp.bar, 1ull);
+  }
+}
 __device__ __forceinline__ int ld_vol(const int* p) { return *(const volatile int*)p; }
 __device__ __forceinline__ void st_vol(int* p, int v) { *(volatile int*)p = v; }
 
@@ -260,27 +286,26 @@ __device__ __noinline__ void issue_obs(const SweepParams& sp, int step, unsigned
 }
 
 // spin until the arrival counter reaches `target` (one thread); false = watchdog / error
-__device__ __noinline__ bool bar_wait(const unsigned long long* bar, unsigned long long target, int* err) {
+__device__ __noinline__ bool bar_wait(const SweepParams& sp, unsigned long long target) {
   const unsigned long long t0 = globaltimer_ns();
   unsigned spins = 0;
-  while (ld_acquire_u64(bar) < target) {
+  while (ld_counter(sp) < target) {
     if (((++spins) & 0x3ffu) == 0) {
-      if (__ldcg(err) != 0) return false;
-      if (globaltimer_ns() - t0 > 4000000000ull) { atomicExch(err, 77); return false; }
+      if (__ldcg(sp.err) != 0) return false;
+      if (globaltimer_ns() - t0 > 4000000000ull) { atomicExch(sp.err, 77); return false; }
     }
   }
-  __threadfence();
+  if (sp.R > 1) __threadfence_system(); else __threadfence();
   return true;
 }
 
 // blocking full grid barrier (resampling only), all threads of the CTA
-__device__ __noinline__ bool grid_sync(unsigned long long* bar, SweepSmem& sm, int G, int* err) {
+__device__ __noinline__ bool grid_sync(const SweepParams& sp, SweepSmem& sm) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    sm.epoch += G;
-    __threadfence();
-    atomicAdd(bar, 1ull);
-    if (!bar_wait(bar, sm.epoch, err)) sm.fail = 1;
+    sm.epoch += (unsigned long long)sp.R * sp.G;  // every CTA of every rank
+    arrive_all(sp);
+    if (!bar_wait(sp, sm.epoch)) sm.fail = 1;
   }
   __syncthreads();
   return sm.fail == 0;
@@ -303,7 +328,7 @@ __device__ __noinline__ void rebuild_rows(const SweepParams& sp, const CtaTables
     }
     if (lane == 0) {
       T.ucount[u] = cnt;
-      T.ulog[u] = ldcg_i32(sp.logical_of + (ev & 1) * sp.P + slot);
+      T.ulog[u] = ldcg_i32(sp.logical_of + (ev & 1) * sp.P + sp.slot0 + slot);
     }
   }
 }
@@ -441,7 +466,7 @@ __device__ __noinline__ double run_item(const SweepParams& sp, const CtaTables& 
 // w = exp(l - max_cta)), by ONE warp; fixed shape -> identical bits in every CTA.
 // Returns ESS <= P/2 (src/pmdi.jl:317); *mx_out = max log-weight.
 __device__ __noinline__ bool resolve_ess(const SweepParams& sp, int st, double* mx_out) {
-  const int lane = threadIdx.x & 31, G = sp.G;
+  const int lane = threadIdx.x & 31, G = sp.R * sp.G;  // CTAs of all ranks
   const double* ep = sp.ess_part + (size_t)(st & 1) * 3 * G;
   double mx = -INFINITY;
 #pragma unroll 1
@@ -472,12 +497,12 @@ __device__ __noinline__ int check_resolved(const SweepParams& sp, SweepSmem& sm,
     const int rs = ld_vol(&sm.res_step);
     if (rs >= s) r = ld_vol(&sm.res_flag) ? 2 : 1;
     else if (rs == s - 1 && ld_vol(&sm.arrived) >= s &&
-             ld_acquire_u64((const unsigned long long*)sp.bar) >= sm.q[s & 1].ep &&
+             ld_counter(sp) >= sm.q[s & 1].ep &&
              atomicCAS(&sm.res_claim, s - 1, s) == s - 1) r = 3;
   }
   r = __shfl_sync(FULL, r, 0);
   if (r == 3) {
-    __threadfence();
+    if (sp.R > 1) __threadfence_system(); else __threadfence();
     TRACE(s + 1, 9)
     double mxv;
     const bool res = resolve_ess(sp, s, &mxv);
@@ -513,14 +538,17 @@ __device__ __noinline__ void cta_arrive(const SweepParams& sp, const CtaTables& 
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
   if (lane == 0) {
-    double* ep = sp.ess_part + ((size_t)(t & 1) * sp.G + blockIdx.x) * 3;
-    __stcg(ep, m); __stcg(ep + 1, s1); __stcg(ep + 2, s2);
+    double* ep = sp.ess_part + ((size_t)(t & 1) * sp.R * sp.G + (size_t)sp.rank * sp.G + blockIdx.x) * 3;
+#pragma unroll 1
+    for (int r = 0; r < sp.R; ++r) {  // every rank's copy of the partials (NVLink peer stores)
+      double* e = on_rank(sp, ep, r);
+      __stcg(e, m); __stcg(e + 1, s1); __stcg(e + 2, s2);
+    }
     issue_obs(sp, t + PMDI_OBS_RING - 1, xring, sm.obs_bar);  // its ring slot held x[t-1]: free now
-    sm.epoch += sp.G;
+    sm.epoch += (unsigned long long)sp.R * sp.G;
     sm.q[t & 1].ep = sm.epoch;
-    __threadfence();
+    arrive_all(sp);
     st_vol(&sm.arrived, t);
-    atomicAdd((unsigned long long*)sp.bar, 1ull);
   }
   __syncwarp();
 }
@@ -613,7 +641,9 @@ __device__ __noinline__ void propose_unit(const SweepParams& sp, const CtaTables
     ds.n[(long long)slot * N + label] = n_new;
     T.pend[u] = label | (n_new << 8);
     T.pe[u] = pos >= 0 ? pos : cnt;
-    sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
+#pragma unroll 1
+    for (int r = 0; r < sp.R; ++r)  // every rank back-traces the selected particle's lineage itself
+      *on_rank(sp, sp.alloc_log + ((size_t)step * K + k) * P + p, r) = (uint8_t)label;
     if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
     atomicAdd(&sm.rows_eval[k], (unsigned)cnt);
   }
@@ -667,7 +697,8 @@ __device__ __noinline__ void propose_unit(const SweepParams& sp, const CtaTables
           ++idx;
         }
       T.lw_s[sl] = w;
-      __stcg(sp.lw + p, w);
+#pragma unroll 1
+      for (int r = 0; r < sp.R; ++r) __stcg(on_rank(sp, sp.lw + p, r), w);  // every rank plans the resampling
       if (sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
       __threadfence_block();
       last_particle = (atomicAdd(&sm.q[par].pdone, 1) == ns - 1) ? 1 : 0;
@@ -689,22 +720,26 @@ __device__ __noinline__ bool do_resample(const SweepParams& sp, const CtaTables&
                                          int st, int* s_tmp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = PMDI_NT / 32;
   const int cta = blockIdx.x, G = sp.G, K = sp.K, N = sp.N;
-  unsigned long long* bar = (unsigned long long*)sp.bar;
   const int ev = sm.ev;
+  // every rank runs the plan on its own copy of the log-weights: same inputs, same plan
   if (cta == 0) resample_plan(sp, st, ev, sm.res_mx, sp.lw, s_tmp);
-  if (!grid_sync(bar, sm, G, sp.err)) return false;
+  if (!grid_sync(sp, sm)) return false;
   const int ncopy = ldcg_i32(sp.plan_out);
   const int gw = cta * NW + warp, GW = G * NW;
 #pragma unroll 1
   for (int idx = gw; idx < ncopy * K * N; idx += GW) {
     const int c = idx / (K * N), rem = idx - c * (K * N);
     const int k = rem / N, m = rem - k * N;
-    const int2 cp = __ldcg(sp.copies + c);
-    row_copy(sp.ds[k], (long long)cp.x * N + m, (long long)cp.y * N + m, lane);
+    const int2 cp = __ldcg(sp.copies + c);  // (source, destination) as GLOBAL slots
+    const int dl = cp.y - sp.slot0;
+    if (dl < 0 || dl >= sp.Ps) continue;     // the rank that holds the destination pulls the row
+    const int sr = cp.x / sp.Ps, sl = cp.x - sr * sp.Ps;
+    if (sr != sp.rank && lane == 0) atomicAdd((unsigned long long*)&sp.counters[3], 1ull);  // pulled over NVLink
+    row_copy(sp.ds[k], sp.peer_delta[sr], (long long)sl * N + m, (long long)dl * N + m, lane);
   }
   for (int sl = tid; sl < ns; sl += PMDI_NT) T.lw_s[sl] = 1.0;  // logweight .= 1.0 (src/pmdi.jl:319)
   if (cta == 0 && tid == 0) { sp.counters[0] += 1; sp.counters[1] += ncopy; }
-  if (!grid_sync(bar, sm, G, sp.err)) return false;
+  if (!grid_sync(sp, sm)) return false;
   if (tid == 0) sm.ev = ev + 1;
   rebuild_rows(sp, T, nu, ev + 1);
   __syncthreads();
@@ -934,7 +969,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
   {
     const int st = steps - 1;
     if (warp == 0) {
-      if (lane == 0 && !bar_wait((const unsigned long long*)sp.bar, sm.q[st & 1].ep, sp.err)) sm.fail = 1;
+      if (lane == 0 && !bar_wait(sp, sm.q[st & 1].ep)) sm.fail = 1;
       __syncwarp();
       if (sm.res_step < st) {
         double mxv;
@@ -951,7 +986,8 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
   }
   __syncthreads();
   if (tid < K) atomicAdd(sp.rows_eval + tid, (unsigned long long)sm.rows_eval[tid]);
-  for (int sl = tid; sl < ns; sl += PMDI_NT) sp.lw_out[T.ulog[sl * K]] = T.lw_s[sl];
+  if (cta == 0)  // every rank holds all P log-weights; after a final resampling they are all 1.0 (:319)
+    for (int p = tid; p < sp.P; p += PMDI_NT) sp.lw_out[p] = sm.res_flag ? 1.0 : __ldcg(sp.lw + p);
   if (timing && tid < 8) sp.phase_ns[(size_t)cta * 8 + tid] = sm.tacc[tid] / NW;
   if (cta == 0 && tid == 0) sp.counters[2] = sm.ev;
 #undef PHASE_MARK

@@ -1,0 +1,81 @@
+"""Particles sharded over the GPUs of one node: R processes, one GPU each, the
+per-observation exchange inside the sweep kernel over NVLink peer memory.  The sharded run must
+reproduce the oracle's run of the GLOBAL particle set: allocations of every step, ancestors,
+selected particle and final allocations bit-exact, on every rank.  Needs >= 2 GPUs
+(`gpurun --gpus 2`); skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+from helpers import C, G, NB, problem, tapes_for
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-5
+
+
+def _n_gpus():
+    try:
+        import pmdi_b200.capi as capi
+        return capi.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+CASES = {
+    # resampling moves particles between the ranks in all of these
+    "mixed_k3": dict(sets=[(G, 130, 0), (C, 65, 3), (NB, 100, 0)], n=120, N=12, P=64),
+    "gauss_manyP": dict(sets=[(G, 64, 0), (NB, 33, 0)], n=64, N=5, P=600),
+    "tiny": dict(sets=[(G, 4, 0)], n=40, N=4, P=4),
+}
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("name", list(CASES))
+def test_sharded_sweep_matches_oracle(name, world, tmp_path):
+    if _n_gpus() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    from oracle import oracle as orc
+    from sharded_worker import run_rank
+    kw, seed, sweeps = CASES[name], 4, 2
+    use_tapes = name == "mixed_k3"
+    mp.spawn(run_rank, args=(world, _free_port(), kw, seed, str(tmp_path), use_tapes, sweeps), nprocs=world, join=True)
+    got = [np.load(os.path.join(tmp_path, f"rank{r}.npz")) for r in range(world)]
+
+    pr = problem(**kw, seed=seed)
+    tapes = tapes_for(pr) if use_tapes else None
+    o = orc.Oracle(pr["data"], pr["types"], pr["N"], pr["P"])
+    s = pr["s"]
+    rng = np.random.default_rng(77)
+    moved = remote = 0
+    for it in range(sweeps):
+        order = pr["order"] if it == 0 else rng.permutation(pr["n"]) + 1
+        ref = o.sweep(s, order, pr["n1"], pr["Pi"], pr["phi"], mode=orc.MODE_DENSE, seed=11, it=3 + it,
+                      logweight_init=0.0 if it == 0 else 1.0, tapes=tapes if it == 0 else None, debug=True)
+        s = ref["s"]
+        for r in range(world):  # every rank returns the same, complete answer
+            np.testing.assert_array_equal(got[r][f"s_{it}"], ref["s"], err_msg=f"rank {r}")
+            assert int(got[r][f"p_star_{it}"]) == ref["p_star"]
+            np.testing.assert_array_equal(got[r][f"anc_{it}"], ref["anc"])
+            assert int(got[r][f"n_resamples_{it}"]) == ref["n_resamples"]
+            np.testing.assert_allclose(got[r][f"logweight_{it}"], ref["logweight"], rtol=RTOL, atol=1e-9)
+        # per-step captures are written by the rank that holds the particle: add the ranks up
+        alloc = sum(got[r][f"alloc_{it}"] for r in range(world))
+        np.testing.assert_array_equal(alloc, ref["alloc"])
+        np.testing.assert_allclose(sum(got[r][f"lw_{it}"] for r in range(world)), ref["lw"], rtol=RTOL, atol=1e-9)
+        np.testing.assert_allclose(sum(got[r][f"lp_{it}"] for r in range(world)), ref["lp"], rtol=RTOL, atol=1e-9)
+        cn = np.max([got[r][f"cluster_n_{it}"] for r in range(world)], axis=0)   # -1 where not held
+        np.testing.assert_array_equal(cn, ref["cluster_n"])
+        assert (cn.sum(axis=2) == pr["n"]).all()
+        moved += int(got[0][f"n_copies_{it}"])
+        remote += sum(int(got[r][f"n_remote_rows_{it}"]) for r in range(world))
+    assert moved > 0    # resampling did duplicate particles ...
+    assert remote > 0   # ... and some of their rows were pulled from another rank's GPU
