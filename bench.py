@@ -121,22 +121,29 @@ def run_reference(args):
     if rank != 0:
         return
     from oracle import oracle as orc
-    cfg = make_workload(args.workload)
+    # the same job as the GPU arm at this N: the configuration's particle count per GPU x GPUs
+    base = make_workload(args.workload, particles=args.particles)
+    cfg = make_workload(args.workload, particles=base["P"] * max(1, args.gpus))
     o = orc.Oracle(cfg["data"], cfg["types"], cfg["N"], cfg["P"])
     hy, n, rng = cfg["hy"], cfg["n"], cfg["rng"]
     mode = orc.MODE_DEDUP | orc.MODE_LITERAL_NEWID
     s = hy["s"]
     times, burn = [], []
+    n_burn = BURN_IN
     for it in range(BURN_IN + args.warmup + args.steps):
+        if it < n_burn and sum(burn) > 150.0:   # bound the whole run: stop burning in, say so below
+            n_burn = it
+        if it >= n_burn + args.warmup + args.steps:
+            break
         order = rng.permutation(n) + 1
         t0 = time.perf_counter()
         r = o.sweep(s, order, cfg["n1"], hy["Pi"], hy["phi"], mode=mode, seed=cfg["seed"], it=it,
                     logweight_init=0.0 if it == 0 else 1.0)
         dt = time.perf_counter() - t0
         s = r["s"]
-        if it < BURN_IN:
+        if it < n_burn:
             burn.append(dt)
-        elif it >= BURN_IN + args.warmup:
+        elif it >= n_burn + args.warmup:
             times.append(dt)
     total = float(np.sum(times))
     dense = dense_evals_per_sweep(cfg)
@@ -150,7 +157,8 @@ def run_reference(args):
         "data": "synthetic",
         "config": {"workload": args.workload, "n_obs": n, "K": cfg["K"], "N": cfg["N"],
                    "particles": cfg["P"], "rho": cfg["rho"],
-                   "chain_state": f"settled: {BURN_IN} untimed burn-in sweeps from the random initial allocation",
+                   "chain_state": f"settled: {n_burn} untimed burn-in sweeps from the random initial allocation"
+                                  + ("" if n_burn == BURN_IN else f" (cut from {BURN_IN} by the 150 s bound)"),
                    "burn_in_sweep_ms": [round(1e3 * v, 1) for v in burn],
                    "note": "restated reference (C++), not Julia: julia is not installed in this image; "
                            "value counts the DENSE evals the sweep stands for, the reference evaluates "
@@ -208,9 +216,14 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    cfg = make_workload(args.workload, seed_shift=rank, particles=args.particles)
+    # Particles are sharded over the GPUs: weak scaling = the configuration's particle
+    # count PER GPU, so the job has P * world particles; every rank passes identical arguments.
+    base = make_workload(args.workload, particles=args.particles)
+    cfg = make_workload(args.workload, particles=base["P"] * world)
     hy, n, K, N, P = cfg["hy"], cfg["n"], cfg["K"], cfg["N"], cfg["P"]
-    ctx = capi.Context(cfg["data"], cfg["types"], N, P, device=local)
+    ctx = capi.Context(cfg["data"], cfg["types"], N, P, device=local, rank=rank, n_ranks=world)
+    if world > 1:
+        ctx.connect()
     stream = torch.cuda.current_stream()
     capi._check(capi.lib().pmdi_ctx_set_stream(ctx.h, stream.cuda_stream))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -221,6 +234,12 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def ranks_ready():
+        """With several ranks every rank's grid counter must be reset (upload) before any rank's
+        kernel starts to arrive on it (include/pmdi_cuda.h)."""
+        if world > 1:
+            dist.barrier()
 
     # ---------------------------------------------------------------- device-resident timing
     # the clock sampler starts BEFORE the warm-up: nvidia-smi's NVML start-up stalls launches on the
@@ -235,8 +254,9 @@ def run_ours(args):
     s = hy["s"]
     burn_ms = []
     for it in range(BURN_IN + args.warmup):
-        ctx.upload(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"] + rank, it=it,
+        ctx.upload(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
                    logweight_init=0.0 if it == 0 else 1.0)
+        ranks_ready()
         flush.zero_()
         ctx.run()
         r = ctx.download()
@@ -255,8 +275,9 @@ def run_ours(args):
     step_ev[0].record(stream)
     for t in range(args.steps):
         it = BURN_IN + args.warmup + t
-        ctx.upload(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"] + rank, it=it,
+        ctx.upload(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
                    logweight_init=1.0)
+        ranks_ready()
         flush.zero_()
         ctx.run()
         step_ev[t + 1].record(stream)
@@ -267,18 +288,20 @@ def run_ours(args):
     r = ctx.download()
     clocks = sampler.stop() if rank == 0 else None
 
+    do_sweep = ctx.sweep_sharded if world > 1 else ctx.sweep
     # per-launch kernel time + work counters: one more pass, sweep by sweep (untimed region)
-    kms, rows_k, resamples, ncopies, evals = [], np.zeros(K), 0, 0, 0
+    kms, rows_k, resamples, ncopies, evals, remote_rows = [], np.zeros(K), 0, 0, 0, 0
     for t in range(args.steps):
         it = BURN_IN + args.warmup + t
         flush.zero_()
-        r = ctx.sweep(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"] + rank, it=it,
-                      logweight_init=1.0, time_phases=(t == args.steps - 1))
+        r = do_sweep(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
+                     logweight_init=1.0, time_phases=(t == args.steps - 1))
         kms.append(r["sweep_kernel_ms"])
         rows_k += np.array(r["rows_evaluated"][:K], dtype=float)
         resamples += r["n_resamples"]
         ncopies += r["n_copies"]
         evals += r["n_evals"]
+        remote_rows += r["n_remote_rows"]
     phase_ms, phase_ms_max = r["phase_ms"], r["phase_ms_max"]
 
     # ---------------------------------------------------------------- end to end (host buffers)
@@ -287,8 +310,8 @@ def run_ours(args):
     s2 = s
     for t in range(args.steps):
         it = BURN_IN + args.warmup + t
-        r2 = ctx.sweep(s2, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"] + rank, it=it,
-                       logweight_init=1.0)
+        r2 = do_sweep(s2, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
+                      logweight_init=1.0)
         s2 = r2["s"]  # the next sweep starts from these allocations, as in pmdi()
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -299,16 +322,21 @@ def run_ours(args):
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t_dev[0]), float(t_dev[1])
-    value = world * dense * args.steps / (dev_ms * 1e-3)
-    e2e_val = world * dense * args.steps / (e2e_ms * 1e-3)
+    # `dense` already counts the whole job (P = particles per GPU x GPUs)
+    value = dense * args.steps / (dev_ms * 1e-3)
+    e2e_val = dense * args.steps / (e2e_ms * 1e-3)
+    evals_t = torch.tensor([float(evals), float(remote_rows)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(evals_t, op=dist.ReduceOp.SUM)
+    evals, remote_rows = float(evals_t[0]), float(evals_t[1])
 
     if rank == 0:
         D = [d.shape[1] for d in cfg["data"]]
         types = cfg["types"]
         alg = sum(rows_k[k] * D[k] * READ_B[types[k]] for k in range(K)) / args.steps + \
-            sum(steps_obs * P * D[k] * ADD_B[types[k]] for k in range(K))
+            sum(steps_obs * (P // world) * D[k] * ADD_B[types[k]] for k in range(K))
         alg_stored = sum(rows_k[k] * D[k] * READ_B_STORED[types[k]] for k in range(K)) / args.steps + \
-            sum(steps_obs * P * D[k] * ADD_B_STORED[types[k]] for k in range(K))
+            sum(steps_obs * (P // world) * D[k] * ADD_B_STORED[types[k]] for k in range(K))
         k_ms = float(np.mean(kms))
         peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(peaks_path):
@@ -319,7 +347,7 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("workload") == args.workload and tj.get("particles") == P:
+            if tj.get("workload") == args.workload and tj.get("particles") == P and world == 1:
                 traffic = tj.get("dram_bytes_per_launch")
         achieved = alg / (k_ms * 1e-3) / 1e9
         h2d = n * K * 8 + n * 4 + N * K * 8 + max(1, K * (K - 1) // 2) * 8
@@ -335,7 +363,13 @@ def run_ours(args):
                                "(the same protocol as the reference arm)",
                 "burn_in_kernel_ms": [round(v, 2) for v in burn_ms],
                 "step": "one full conditional-SMC sweep (prefix build, per-observation loop, selection)",
-                "parallelism": "single GPU" if world == 1 else f"{world} independent chains (replicas), one per GPU",
+                "parallelism": "single GPU" if world == 1 else
+                               f"one chain, {P} particles sharded over {world} GPUs ({P // world} per GPU): ESS partials, "
+                               "log-weights and allocations exchanged per observation with NVLink peer stores inside the "
+                               "sweep kernel, resampled ancestors pulled through peer memory; a host barrier between "
+                               "upload and run of every sweep",
+                "particles_per_gpu": P // world,
+                "rows_pulled_from_peers_per_sweep": remote_rows / args.steps,
                 "l2": "256 MiB buffer written between timed sweeps (L2 flush); per-particle statistics "
                       f"{sum(P * N * D[k] * (32 if types[k] == 0 else 8) for k in range(K)) / 1e6:.0f} MB > 126 MB L2",
                 "empty_clusters": "labels with n == 0 share one evaluation per step (same result as evaluating "
@@ -351,7 +385,8 @@ def run_ours(args):
                     "path": "pmdi_sweep() C-ABI call with host buffers, allocations chained sweep to sweep"},
             "gpu_launches": 7 * args.steps,
             "roofline": {
-                "bound": "hbm", "kernel": "k_sweep (persistent, one launch per sweep)",
+                "bound": "hbm", "kernel": "k_sweep (persistent, one launch per sweep)" +
+                                          ("" if world == 1 else "; rank 0's launch and rank 0's own particles"),
                 "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": peak_src, "traffic": traffic,
                 "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,

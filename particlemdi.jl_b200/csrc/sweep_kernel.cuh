@@ -468,16 +468,40 @@ __device__ __noinline__ double run_item(const SweepParams& sp, const CtaTables& 
 __device__ __noinline__ bool resolve_ess(const SweepParams& sp, int st, double* mx_out) {
   const int lane = threadIdx.x & 31, G = sp.R * sp.G;  // CTAs of all ranks
   const double* ep = sp.ess_part + (size_t)(st & 1) * 3 * G;
+  // One partial per CTA of every rank (148 on one GPU, 1184 on eight).  The loads go out in batches
+  // of 8 per lane so that a batch costs ONE L2 round trip; the accumulation order is fixed, so every
+  // CTA of every rank gets the same bits.
   double mx = -INFINITY;
 #pragma unroll 1
-  for (int c = lane; c < G; c += 32) mx = fmax(mx, ldcg_f64(ep + 3 * c));
+  for (int base = 0; base < G; base += 256) {
+    double m[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = base + lane + 32 * i;
+      m[i] = (c < G) ? ldcg_f64(ep + 3 * c) : -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmax(mx, m[i]);
+  }
   mx = warp_max(mx);
   double num = 0.0, den = 0.0;
 #pragma unroll 1
-  for (int c = lane; c < G; c += 32) {
-    const double e = pm_exp(ldcg_f64(ep + 3 * c) - mx);
-    num += ldcg_f64(ep + 3 * c + 1) * e;
-    den += ldcg_f64(ep + 3 * c + 2) * (e * e);
+  for (int base = 0; base < G; base += 256) {
+    double m[8], s1[8], s2[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = base + lane + 32 * i;
+      const bool ok = c < G;
+      m[i] = ok ? ldcg_f64(ep + 3 * c) : -INFINITY;  // exp(-inf) = 0 pads
+      s1[i] = ok ? ldcg_f64(ep + 3 * c + 1) : 0.0;
+      s2[i] = ok ? ldcg_f64(ep + 3 * c + 2) : 0.0;
+    }
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      const double e = pm_exp(m[i] - mx);
+      num += s1[i] * e;
+      den += s2[i] * (e * e);
+    }
   }
   num = warp_sum(num);
   den = warp_sum(den);
