@@ -33,11 +33,11 @@ CASES = {
     # resampling moves particles between the ranks in all of these
     "mixed_k3": dict(sets=[(G, 130, 0), (C, 65, 3), (NB, 100, 0)], n=120, N=12, P=64),
     "gauss_manyP": dict(sets=[(G, 64, 0), (NB, 33, 0)], n=64, N=5, P=600),
-    "tiny": dict(sets=[(G, 4, 0)], n=40, N=4, P=4),
+    "tiny": dict(sets=[(G, 4, 0)], n=40, N=4, P=8),   # one particle per rank at 8 ranks
 }
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("name", list(CASES))
 def test_sharded_sweep_matches_oracle(name, world, tmp_path):
     if _n_gpus() < world:
