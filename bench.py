@@ -347,8 +347,9 @@ def run_ours(args):
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             tj = json.load(open(tpath))
-            if tj.get("workload") == args.workload and tj.get("particles") == P and world == 1:
-                traffic = tj.get("dram_bytes_per_launch")
+            for e in (tj if isinstance(tj, list) else [tj]):  # ncu captures, one entry per workload
+                if e.get("workload") == args.workload and e.get("particles") == P and world == 1:
+                    traffic = e.get("dram_bytes_per_launch")
         achieved = alg / (k_ms * 1e-3) / 1e9
         h2d = n * K * 8 + n * 4 + N * K * 8 + max(1, K * (K - 1) // 2) * 8
         d2h = n * K * 8 + P * 8 + K * P * N * 8 + 8 + 4 + 32 + 64 + 64
