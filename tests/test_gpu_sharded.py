@@ -30,11 +30,13 @@ def _free_port():
 
 
 CASES = {
-    # resampling moves particles between the ranks in all of these
     "mixed_k3": dict(sets=[(G, 130, 0), (C, 65, 3), (NB, 100, 0)], n=120, N=12, P=64),
     "gauss_manyP": dict(sets=[(G, 64, 0), (NB, 33, 0)], n=64, N=5, P=600),
     "tiny": dict(sets=[(G, 4, 0)], n=40, N=4, P=8),   # one particle per rank at 8 ranks
 }
+# cases in which resampling is known to duplicate particles (and so to pull rows between ranks);
+# "tiny" checks parity with one particle per rank and happens not to duplicate any
+MOVES = {"mixed_k3", "gauss_manyP"}
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])
@@ -77,5 +79,6 @@ def test_sharded_sweep_matches_oracle(name, world, tmp_path):
         assert (cn.sum(axis=2) == pr["n"]).all()
         moved += int(got[0][f"n_copies_{it}"])
         remote += sum(int(got[r][f"n_remote_rows_{it}"]) for r in range(world))
-    assert moved > 0    # resampling did duplicate particles ...
-    assert remote > 0   # ... and some of their rows were pulled from another rank's GPU
+    if name in MOVES:
+        assert moved > 0    # resampling did duplicate particles ...
+        assert remote > 0   # ... and some of their rows were pulled from another rank's GPU
