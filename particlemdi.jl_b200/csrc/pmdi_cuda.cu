@@ -340,7 +340,10 @@ int fill_params(pmdi_ctx* c) {
   sp.cta_off = c->d_cta_off.p; sp.cta_units = c->d_cta_units.p;
   sp.max_units = c->max_units; sp.sm_x_bytes = c->sm_x_bytes; sp.lf_T = c->lf_T;
   sp.item_cap = c->item_cap; sp.lf_glob = c->lf_dev.p; sp.lf_glob_T = c->lf_want;
-  sp.qb = getenv("PMDI_QB") ? std::max(1, atoi(getenv("PMDI_QB"))) : 2;
+  // 256-feature blocks per plain work item.  With few units per CTA rows have to be split so that the 16
+  // warps have work (cfg2, 6 units: 1-2 blocks best, 3 already +3 %); with many units a whole row per item
+  // is best (cfg4, 14 units: 8 blocks 9 % faster than 2) - profiles/r01_k_sweep_cfg4.md.  PMDI_QB overrides.
+  sp.qb = getenv("PMDI_QB") ? std::max(1, atoi(getenv("PMDI_QB"))) : (c->max_units >= 11 ? std::max(2, c->Jmax) : 2);
   return 0;
 }
 

@@ -82,6 +82,17 @@ def test_sweep_with_feature_flags():
     _assert_parity(pr, ref, got)
 
 
+@pytest.mark.parametrize("name", ["gauss_wide", "mixed_k3", "mixed_k2_manyP"])
+@pytest.mark.parametrize("qb", ["1", "8"])
+def test_parity_for_other_item_sizes(name, qb, monkeypatch):
+    """The number of 256-feature blocks per plain work item is chosen per workload (whole rows when a
+    CTA owns many units); parity must not depend on it."""
+    monkeypatch.setenv("PMDI_QB", qb)
+    pr = problem(**CASES[name], seed=5)
+    ref, got = _run_both(pr, lw0=1.0)
+    _assert_parity(pr, ref, got)
+
+
 def test_sstar_compat_flag():
     """pmdi()'s own (unpermuted) trajectory emission, src/pmdi.jl:321-324."""
     from oracle import oracle as orc
