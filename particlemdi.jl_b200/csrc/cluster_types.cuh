@@ -488,70 +488,36 @@ __device__ __forceinline__ double cat_eval_item(const DsDev& ds, long long row, 
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void row_copy(const DsDev& ds, long long sdelta, long long src, long long dst, int lane) {
   // sdelta: byte offset from this rank's arena to the arena of the rank that holds the source row
-  // (0 when it is local); the source is read through NVLink peer memory then.  Loads go out FOUR
-  // 64-feature steps at a time before the first store: a store between two loads stops the compiler
-  // from overlapping them, and over NVLink every serialized step is a multi-microsecond round trip.
+  // (0 when it is local); the source is read through NVLink peer memory then.
 #define PMDI_SRC(ptr_) ((decltype(ptr_))((const char*)(ptr_) + sdelta))
   const int ns = ldcg_i32(PMDI_SRC(ds.n) + src), nd = ldcg_i32(ds.n + dst);
   if (ns == 0 && nd == 0) return;
   const int Dp = ds.Dp;
   if (ds.type == T_GAUSSIAN) {
-    const double* sa[4] = {PMDI_SRC(ds.mu) + src * Dp, PMDI_SRC(ds.lamn) + src * Dp,
-                           PMDI_SRC(ds.sum) + src * Dp, PMDI_SRC(ds.beta) + src * Dp};
-    double* da[4] = {ds.mu + dst * Dp, ds.lamn + dst * Dp, ds.sum + dst * Dp, ds.beta + dst * Dp};
-    const double init[4] = {0.0, 1.0, 0.0, 0.5};  // the empty cluster (gaussian_cluster.jl:17-21)
-#pragma unroll 1
-    for (int q0 = 2 * lane; q0 < Dp; q0 += 256) {
-      double2 v[4][4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int q = q0 + 64 * i;
-          v[i][a] = (ns && q < Dp) ? ldcg_f64x2(sa[a] + q) : make_double2(init[a], init[a]);
-        }
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int a = 0; a < 4; ++a) {
-          const int q = q0 + 64 * i;
-          if (q < Dp) *(double2*)(da[a] + q) = v[i][a];
-        }
+    for (int q = 2 * lane; q < Dp; q += 64) {
+      double2 a, b, c, d;
+      if (ns) {
+        a = ldcg_f64x2(PMDI_SRC(ds.mu) + src * Dp + q); b = ldcg_f64x2(PMDI_SRC(ds.lamn) + src * Dp + q);
+        c = ldcg_f64x2(PMDI_SRC(ds.sum) + src * Dp + q); d = ldcg_f64x2(PMDI_SRC(ds.beta) + src * Dp + q);
+      } else {
+        a = make_double2(0.0, 0.0); b = make_double2(1.0, 1.0);
+        c = make_double2(0.0, 0.0); d = make_double2(0.5, 0.5);
+      }
+      *(double2*)(ds.mu + dst * Dp + q) = a; *(double2*)(ds.lamn + dst * Dp + q) = b;
+      *(double2*)(ds.sum + dst * Dp + q) = c; *(double2*)(ds.beta + dst * Dp + q) = d;
     }
   } else if (ds.type == T_CATEGORICAL) {
     const long long W = (long long)ds.Lmax * Dp;
-    const uint32_t* sc = PMDI_SRC(ds.cnt) + src * W;
-    uint32_t* dc = ds.cnt + dst * W;
-#pragma unroll 1
-    for (long long q0 = 4 * lane; q0 < W; q0 += 512) {
-      uint4 v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long q = q0 + 128 * i;
-        v[i] = (ns && q < W) ? __ldcg((const uint4*)(sc + q)) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const long long q = q0 + 128 * i;
-        if (q < W) *(uint4*)(dc + q) = v[i];
-      }
+    for (long long q = 4 * lane; q < W; q += 128) {
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (ns) v = __ldcg((const uint4*)(PMDI_SRC(ds.cnt) + src * W + q));
+      *(uint4*)(ds.cnt + dst * W + q) = v;
     }
   } else {
-    const long long* ss = PMDI_SRC(ds.S) + src * Dp;
-    long long* dS = ds.S + dst * Dp;
-#pragma unroll 1
-    for (int q0 = 2 * lane; q0 < Dp; q0 += 256) {
-      longlong2 v[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int q = q0 + 64 * i;
-        v[i] = (ns && q < Dp) ? ldcg_i64x2(ss + q) : make_longlong2(0, 0);
-      }
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int q = q0 + 64 * i;
-        if (q < Dp) *(longlong2*)(dS + q) = v[i];
-      }
+    for (int q = 2 * lane; q < Dp; q += 64) {
+      longlong2 v = make_longlong2(0, 0);
+      if (ns) v = ldcg_i64x2(PMDI_SRC(ds.S) + src * Dp + q);
+      *(longlong2*)(ds.S + dst * Dp + q) = v;
     }
   }
   for (int j = lane; j < ds.J; j += 32) ds.aux[dst * ds.J + j] = ns ? ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + j) : 0.0;
