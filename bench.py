@@ -384,7 +384,7 @@ def run_ours(args):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "path": "pmdi_sweep() C-ABI call with host buffers, allocations chained sweep to sweep"},
-            "gpu_launches": 7 * args.steps,
+            "gpu_launches": 8 * args.steps,  # per sweep: sweep_init, prefix_lists, prefix_build, proto_aux, broadcast, empty_lp, k_sweep, finish
             "roofline": {
                 "bound": "hbm", "kernel": "k_sweep (persistent, one launch per sweep)" +
                                           ("" if world == 1 else "; rank 0's launch and rank 0's own particles"),
