@@ -67,3 +67,61 @@ def test_pmdi_feature_select_and_single_dataset(tmp_path):
     flines = fs.read_text().strip().split("\n")
     assert flines[0].split(",") == [f"K1_d{d}" for d in range(1, 13)]
     assert len(flines) == 1 + 1 + 6 and set(",".join(flines[1:]).split(",")) <= {"true", "false"}
+
+
+def _oracle_driven_chain(data, types, N, P, rho, iters, seed):
+    """The loop of pmdi() (particlemdi.jl_b200/pmdi.py) with the ORACLE doing the sweeps: same host
+    functions, same order of host random draws.  Test infrastructure; returns the allocations after
+    every iteration (the CSV rows of pmdi() with thin = 1)."""
+    import math
+    from oracle import oracle as orc
+    from pmdi_b200 import pmdi as host
+    K, n = len(data), data[0].shape[0]
+    rng = np.random.default_rng(seed)
+    M = np.full(K, 2.0)
+    gamma = rng.gamma(1.0 / N, 1.0, (N, K)) + host.EPS
+    phi = rng.gamma(1.0, 0.2, K * (K - 1) // 2) if K > 1 else np.zeros(1)
+    s = np.stack([1 + rng.choice(N, size=n, p=gamma[:, k] / gamma[:, k].sum()) for k in range(K)],
+                 axis=1).astype(np.int64)
+    tables = host.HyperTables(N, K)
+    tables.refresh(gamma)
+    v = host.update_v(n, host.update_Z(phi, tables), rng)
+    o = orc.Oracle(data, types, N, P)
+    n1 = int(math.floor(rho * n))
+    rows = [s.copy()]
+    for it in range(1, iters + 1):
+        order = rng.permutation(n) + 1
+        host.update_M(M, gamma, K, N, rng)
+        tables.refresh(gamma)
+        host.update_gamma(gamma, phi, v, M, s, tables, rng)
+        Pi = gamma / gamma.sum(axis=0, keepdims=True)
+        tables.refresh(gamma)
+        if K > 1:
+            host.update_phi(phi, v, s, tables, rng)
+        v = host.update_v(n, host.update_Z(phi, tables), rng)
+        r = o.sweep(s, order, n1, Pi, phi, mode=orc.MODE_DENSE, logweight_init=0.0 if it == 1 else 1.0,
+                    seed=seed, it=it)
+        s = np.array(r["s"], dtype=np.int64, order="C")
+        host.align_labels(s, phi, gamma, N, K, rng)
+        rows.append(s.copy())
+    return rows
+
+
+def test_pmdi_chain_equals_oracle_driven_loop(tmp_path):
+    """Deterministic mode over a whole run: pmdi() on the GPU and the same loop driven by the oracle
+    emit identical allocations at every iteration although Pi and Phi change every iteration - i.e.
+    no float-induced draw flip in any of the draws of the run (the count is printed)."""
+    import pmdi_b200  # noqa: F401
+    from pmdi_b200 import pmdi as host
+    n, K, N, P, iters, seed = 70, 3, 6, 24, 25, 3
+    data, z = _separable(n, seed=5)
+    types = [0, 2, 1]
+    out = tmp_path / "o.csv"
+    host.pmdi(data, types, N, P, 0.25, iters, str(out), seed=seed)
+    got = host.read_allocations(str(out), K, n)
+    want = _oracle_driven_chain(data, types, N, P, 0.25, iters, seed)
+    assert got.shape[0] == iters + 1
+    for it in range(iters + 1):
+        np.testing.assert_array_equal(got[it], want[it], err_msg=f"iteration {it}")
+    steps = n - int(np.floor(0.25 * n)) + 1
+    print(f"0 draw flips in {iters * steps * K * (P - 1)} allocation draws ({iters} iterations)")
