@@ -113,8 +113,9 @@ typedef struct pmdi_sweep_out {
   int64_t  n_resamples;   /* resampling events in this sweep                                  */
   int64_t  n_copies;      /* particle stat blocks moved by resampling (all ranks)             */
   int64_t  n_remote_rows; /* cluster rows this rank pulled from another rank's GPU (NVLink)   */
-  int64_t  n_evals;       /* particle*cluster*feature predictive terms actually evaluated (occupied
-                             clusters only; every empty label shares one evaluation per step) */
+  int64_t  n_evals;       /* cluster*feature predictive terms actually evaluated: every distinct cluster
+                             once per observation (the reference's calc_logprob calls, src/__pmdi.jl:187,
+                             times D_k); all empty labels share one evaluation per step        */
   int64_t  n_evals_dense; /* steps * P * N * sum_k D_k: the dense count of SURVEY.md 8(d)      */
   int64_t  rows_evaluated[8]; /* per dataset: cluster rows evaluated over the sweep           */
   double   device_ms;     /* device time of the whole sweep (prefix .. selection), CUDA events */
@@ -130,6 +131,17 @@ typedef struct pmdi_sweep_out {
   int32_t* dbg_anc;       /* [steps][P] 1-based ancestors, 0 when the step did not resample   */
   int64_t* cluster_n;     /* [K][P][N] occupancy of every particle's clusters after the sweep
                              (-1 for particles held by another rank) */
+  /* device reductions over the NEW allocations for the host's update_hypers (may be NULL):      */
+  int64_t* label_counts;  /* N x K column-major: observations per (label, dataset) = countn(s[:,k], N),
+                             src/update_hypers.jl:72                                            */
+  int64_t* pair_agree;    /* K(K-1)/2, pair order (1,2),(1,3)..: observations with equal labels in
+                             both datasets, src/update_hypers.jl:109-115                        */
+  int64_t  rows_referenced[8]; /* per dataset: occupied (particle, label) clusters the proposals read;
+                             rows_evaluated counts each physical row once per observation       */
+  int32_t  engine;        /* 1 copy-on-write pool, 0 dense                                     */
+  int64_t  rows_evaluated_ahead; /* pool engine: rows evaluated for observation t+1 before the resampling
+                             decision of step t removed them (evaluation runs ahead of the ESS test);
+                             rows_evaluated - rows_evaluated_ahead = the reference's calc_logprob calls */
 } pmdi_sweep_out;
 
 /*

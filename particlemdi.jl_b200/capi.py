@@ -62,6 +62,8 @@ class SweepOut(C.Structure):
         ("phase_ms_max", C.c_double * 8),
         ("dbg_lp", C.c_void_p), ("dbg_lw", C.c_void_p), ("dbg_alloc", C.c_void_p),
         ("dbg_anc", C.c_void_p), ("cluster_n", C.c_void_p),
+        ("label_counts", C.c_void_p), ("pair_agree", C.c_void_p),
+        ("rows_referenced", C.c_int64 * 8), ("engine", C.c_int32), ("rows_evaluated_ahead", C.c_int64),
     ]
 
 
@@ -255,8 +257,11 @@ class Context:
             "p_star": np.zeros(1, dtype=np.int64),
             "logweight": np.zeros(P),
             "cluster_n": np.zeros((K, P, N), dtype=np.int64),
+            "label_counts": np.zeros((N, K), dtype=np.int64, order="F"),
+            "pair_agree": np.zeros(max(1, K * (K - 1) // 2), dtype=np.int64),
         }
         o = SweepOut()
+        o.label_counts, o.pair_agree = _ptr(res["label_counts"]), _ptr(res["pair_agree"])
         o.s, o.p_star, o.logweight = _ptr(res["s"]), _ptr(res["p_star"]), _ptr(res["logweight"])
         o.cluster_n = _ptr(res["cluster_n"])
         if debug:
@@ -277,6 +282,9 @@ class Context:
         res["n_evals"] = int(o.n_evals)
         res["n_evals_dense"] = int(o.n_evals_dense)
         res["rows_evaluated"] = [int(v) for v in o.rows_evaluated]
+        res["rows_referenced"] = [int(v) for v in o.rows_referenced]
+        res["engine"] = "pool" if o.engine else "dense"
+        res["rows_evaluated_ahead"] = int(o.rows_evaluated_ahead)
         res["device_ms"] = float(o.device_ms)
         res["sweep_kernel_ms"] = float(o.sweep_kernel_ms)
         res["phase_ms"] = [float(v) for v in o.phase_ms]

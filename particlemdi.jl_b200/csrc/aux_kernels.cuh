@@ -3,7 +3,7 @@
 // the feature-selection log-marginal reduction (src/pmdi.jl:120-128,354-370) and the
 // single-cluster evaluation used by the plugin-contract parity tests.
 #pragma once
-#include "cluster_types.cuh"
+#include "pool_types.cuh"
 
 // all rows of a dataset to the empty-cluster state (constructors gaussian_cluster.jl:17-21,
 // categorical_cluster.jl:6-10, negbinom_cluster.jl:9-10)
@@ -33,9 +33,9 @@ __global__ void k_sweep_init(SweepParams sp) {
   }
   if (t == 0) {
     *sp.err = 0;
-    sp.counters[0] = sp.counters[1] = sp.counters[2] = sp.counters[3] = 0;
+    for (int i = 0; i < 8; ++i) sp.counters[i] = 0;
     sp.plan_out[0] = 0;
-    for (int k = 0; k < PMDI_MAX_K; ++k) sp.rows_eval[k] = 0ull;
+    for (int k = 0; k < PMDI_MAX_K; ++k) { sp.rows_eval[k] = 0ull; sp.rows_ref[k] = 0ull; }
   }
 }
 
@@ -68,7 +68,7 @@ __global__ void k_prefix_lists(SweepParams sp, int* members /* [K][n1-1] */, int
 
 // Sequential cluster_add! of the members of one label into row (slot*N + m), one thread per
 // feature (literal arithmetic, same bits as the reference).  use_flags = 0 -> all features on.
-__device__ __forceinline__ void build_row_feature(const DsDev& ds, long long row, int q,
+__device__ __forceinline__ void build_row_feature(const DsDev& ds, const PoolDev* pd, long long row, int q,
                                                   const int* mem, int cnt, int use_flags) {
   const bool on = use_flags ? (ds.flag[q] != 0) : (q < ds.D);
   if (ds.type == T_GAUSSIAN) {
@@ -91,6 +91,17 @@ __device__ __forceinline__ void build_row_feature(const DsDev& ds, long long row
     ds.sum[o] = sum; ds.beta[o] = beta; ds.mu[o] = mu;
     ds.lamn[o] = __ddiv_rn(lam, __dadd_rn((double)cnt, 1.0));
     if (!on || cnt == 0) ds.lamn[o] = 1.0;
+  } else if (ds.type == T_CATEGORICAL && pd) {  // pool engine: packed counts cw[row][q][wpf]
+    unsigned long long* w = pd->cw + ((size_t)row * ds.Dp + q) * pd->wpf;
+    for (int i = 0; i < pd->wpf; ++i) w[i] = 0ull;
+    if (on) {
+      const int* x = (const int*)ds.x;
+      const int fw = 64 / pd->fpw;
+      for (int t = 0; t < cnt; ++t) {
+        const int lv = x[(size_t)mem[t] * ds.Dp + q] - 1;
+        w[lv / pd->fpw] += 1ull << ((lv % pd->fpw) * fw);
+      }
+    }
   } else if (ds.type == T_CATEGORICAL) {
     uint32_t* c = ds.cnt + row * (long long)ds.Lmax * ds.Dp + q;
     for (int l = 0; l < ds.Lmax; ++l) c[(long long)l * ds.Dp] = 0u;
@@ -117,8 +128,8 @@ __global__ void k_prefix_build(SweepParams sp, const int* members, const int* of
   const DsDev& ds = sp.ds[k];
   if (q >= ds.Dp) return;
   const int b = off[k * (sp.N + 1) + m], e = off[k * (sp.N + 1) + m + 1];
-  const long long row = (long long)sp.Ps * sp.N + m;
-  build_row_feature(ds, row, q, members + (size_t)k * (sp.n1 - 1) + b, e - b, 1);
+  const long long row = sp.proto_base + m;
+  build_row_feature(ds, sp.engine ? &sp.pd[k] : nullptr, row, q, members + (size_t)k * (sp.n1 - 1) + b, e - b, 1);
   if (q == 0) ds.n[row] = e - b;
 }
 
@@ -126,7 +137,7 @@ __global__ void k_prefix_build(SweepParams sp, const int* members, const int* of
 __global__ void k_proto_aux(SweepParams sp) {
   const int k = blockIdx.y, m = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const DsDev& ds = sp.ds[k];
-  const long long row = (long long)sp.Ps * sp.N + m;
+  const long long row = sp.proto_base + m;
   const int n = ds.n[row];
   for (int j = w; j < ds.J; j += blockDim.x >> 5) {
     if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);
@@ -146,59 +157,6 @@ __global__ void k_broadcast(SweepParams sp) {
     const long long rem = idx - (long long)k * sp.Ps * sp.N;
     const int m = (int)(rem % sp.N);
     row_copy(sp.ds[k], 0, (long long)sp.Ps * sp.N + m, rem, lane);
-  }
-}
-
-// Particle selection (StatsBase.sample(1:P, Weights(w)), src/pmdi.jl:345-350), lineage back-trace
-// and s[:] = sstar[p_star,:,:] (src/pmdi.jl:373).  One block.
-__global__ void k_finish(SweepParams sp, int compat, long long* s_out, long long* p_star_out,
-                         long long* cluster_n, int* cur_at) {
-  const int t = threadIdx.x, NT = blockDim.x, P = sp.P, K = sp.K, N = sp.N;
-  __shared__ double red[32];
-  double mx = -INFINITY;
-  for (int p = t; p < P; p += NT) mx = fmax(mx, sp.lw_out[p]);
-  mx = warp_max(mx);
-  if ((t & 31) == 0) red[t >> 5] = mx;
-  __syncthreads();
-  mx = red[0];
-  for (int i = 1; i < (NT >> 5); ++i) mx = fmax(mx, red[i]);
-  for (int p = t; p < P; p += NT) sp.sc_w[p] = exp(sp.lw_out[p] - mx);
-  __syncthreads();
-  if (t == 0) {
-    double tot = 0.0;
-    for (int p = 0; p < P; ++p) tot += sp.sc_w[p];
-    const double u = sp.tape_select ? sp.tape_select[0]
-                                    : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_SELECT, 0, 0, 0);
-    const double thr = u * tot;
-    int i = 0;
-    double cw = sp.sc_w[0];
-    while (cw < thr && i < P - 1) { ++i; cw += sp.sc_w[i]; }
-    *p_star_out = i + 1;
-    // lineage of p_star through the resampling events, backwards (src/__pmdi.jl:285)
-    int cur = i;
-    for (int st = sp.steps - 1; st >= 0; --st) {
-      const int ev = sp.ev_of_step[st];
-      if (ev >= 0 && !compat) cur = sp.anc_log[(size_t)ev * P + cur] - 1;
-      cur_at[st] = cur;
-    }
-  }
-  for (size_t i = t; i < (size_t)K * sp.n_obs; i += NT) s_out[i] = sp.s_in[i];
-  __syncthreads();
-  for (int idx = t; idx < sp.steps * K; idx += NT) {
-    const int st = idx / K, k = idx - st * K;
-    const int obs = sp.order[sp.n1 - 1 + st];
-    s_out[(size_t)k * sp.n_obs + obs] = 1 + sp.alloc_log[((size_t)st * K + k) * P + cur_at[st]];
-  }
-  if (cluster_n) {
-    const int ev = (int)sp.counters[2];
-    const int* slot = sp.slot_of + (ev & 1) * P;
-    for (size_t idx = t; idx < (size_t)K * P * N; idx += NT) {
-      const int k = (int)(idx / ((size_t)P * N));
-      const size_t rem = idx - (size_t)k * P * N;
-      const int p = (int)(rem / N), m = (int)(rem % N);
-      const int ls = slot[p] - sp.slot0;  // clusters of particles held by another rank: -1
-      cluster_n[idx] = (ls >= 0 && ls < sp.Ps) ? sp.ds[k].n[(long long)ls * N + m] : -1;
-    }
   }
 }
 
@@ -280,12 +238,19 @@ __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
     for (int q = lane; q < ds.Dp; q += 32) ((int*)xs_raw)[q] = ds.flag[q] ? src[q] : skip;
   }
   __syncwarp();
-  const long long row = (long long)sp.Ps * sp.N;
+  const long long row = sp.proto_base;
   const int n = ds.n[row];
   double acc = ds.rc[n];
   for (int j = 0; j < ds.J; ++j) {
     double v;
     if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, n, (const double*)xs_raw, lane);
+    else if (ds.type == T_CATEGORICAL && sp.engine) {
+      const PoolDev& pd = sp.pd[k];
+      const int base = j * PMDI_FB + 2 * lane;
+      const int nits = min(PMDI_FB / PMDI_WF, (ds.Dp - j * PMDI_FB) / PMDI_WF);
+      v = cat_eval_pool(pd.cw + ((size_t)row * ds.Dp + base) * pd.wpf, pd.wpf, pd.fpw,
+                        (unsigned)__cvta_generic_to_shared(xs_raw) + base * 4u, nits);
+    }
     else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)xs_raw, lane);
     else v = nb_eval_block(ds, row, j, n, (const int*)xs_raw, lane, sp.lf_glob, sp.lf_glob_T);
     acc += v;
@@ -298,14 +263,14 @@ __global__ void k_build_one(SweepParams sp, int k, const int* members, int cnt) 
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const DsDev& ds = sp.ds[k];
   if (q >= ds.Dp) return;
-  const long long row = (long long)sp.Ps * sp.N;
-  build_row_feature(ds, row, q, members, cnt, 1);
+  const long long row = sp.proto_base;
+  build_row_feature(ds, sp.engine ? &sp.pd[k] : nullptr, row, q, members, cnt, 1);
   if (q == 0) ds.n[row] = cnt;
 }
 __global__ void k_aux_one(SweepParams sp, int k) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const DsDev& ds = sp.ds[k];
-  const long long row = (long long)sp.Ps * sp.N;
+  const long long row = sp.proto_base;
   const int n = ds.n[row];
   for (int j = w; j < ds.J; j += blockDim.x >> 5) {
     if (ds.type == T_GAUSSIAN) gauss_aux_block(ds, row, j, lane);

@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
-#include "sweep_kernel.cuh"
+#include "pool_kernel.cuh"
 
 namespace {
 
@@ -76,10 +76,16 @@ struct Dataset {
   DevBuf<uint32_t> cnt;
   DevBuf<long long> S;
   DevBuf<int> n;
+  // pool engine (PoolDev)
+  int cap = 0, wpf = 1, fpw = 4;
+  DevBuf<unsigned long long> cw;
+  DevBuf<int> p_refcnt, p_chosen, p_dst, p_neval, p_live, p_free, p_rowmap, p_ctr;
   void release() {
     x.release(); xq.release(); d_flag.release(); rc.release(); d_nlevels.release();
     mu.release(); lamn.release(); sum.release(); beta.release(); part.release(); aux.release();
-    cnt.release(); S.release(); n.release();
+    cnt.release(); S.release(); n.release(); cw.release();
+    p_refcnt.release(); p_chosen.release(); p_dst.release(); p_neval.release(); p_live.release();
+    p_free.release(); p_rowmap.release(); p_ctr.release();
   }
 };
 
@@ -99,6 +105,9 @@ struct pmdi_ctx {
   unsigned char* arena = nullptr;
   size_t arena_bytes = 0;
   int rank = 0, R = 1, Ps = 0;  // this rank, ranks, particle slots held here (P / R)
+  int engine = 1;               // 1 pool (copy-on-write rows, pool_kernel.cuh), 0 dense (sweep_kernel.cuh)
+  int obs_ring = PMDI_OBS_RING;
+  unsigned long long wd_ns = 10000000000ull;
   long long peer_delta[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   // static layout
@@ -119,7 +128,9 @@ struct pmdi_ctx {
   DevBuf<uint8_t> lab, alloc_log;
   DevBuf<int2> copies;
   DevBuf<unsigned> bar;
-  DevBuf<unsigned long long> rows_eval, phase_ns, trace;
+  DevBuf<unsigned long long> rows_eval, rows_ref, phase_ns, trace;
+  DevBuf<long long> label_counts, pair_agree;
+  DevBuf<double> rank_part;
   DevBuf<double> dbg_lp, dbg_lw, scratch_d;
   DevBuf<int> dbg_alloc, dbg_anc, scratch_i, wd_state;
   DevBuf<uint8_t> scratch_u8;
@@ -147,6 +158,14 @@ void fill_dsdev(pmdi_ctx* c, int k, DsDev& d) {
   d.xstage = (s.type != T_GAUSSIAN && nflag != s.D) ? (const void*)s.xq.p : (const void*)s.x.p;
   d.mu = s.mu.p; d.lamn = s.lamn.p; d.sum = s.sum.p; d.beta = s.beta.p;
   d.cnt = s.cnt.p; d.S = s.S.p; d.part = s.part.p; d.aux = s.aux.p; d.n = s.n.p;
+}
+
+void fill_pooldev(pmdi_ctx* c, int k, PoolDev& d) {
+  Dataset& s = c->ds[k];
+  std::memset(&d, 0, sizeof(d));
+  d.cap = s.cap; d.wpf = s.wpf; d.fpw = s.fpw;
+  d.refcnt = s.p_refcnt.p; d.chosen = s.p_chosen.p; d.dst = s.p_dst.p; d.n_eval = s.p_neval.p;
+  d.live = s.p_live.p; d.freelist = s.p_free.p; d.rowmap = s.p_rowmap.p; d.ctr = s.p_ctr.p; d.cw = s.cw.p;
 }
 
 // x-independent row constants by cluster size n:
@@ -220,7 +239,16 @@ int build_layout(pmdi_ctx* c) {
   c->Ps = c->P / c->R;
   if (c->R > 1 && c->peer_base[c->rank] != nullptr)
     return fail(1, "pmdi: datasets cannot be re-bound after pmdi_ipc_export (the peers hold this layout)");
-  const long long rows = (long long)(c->Ps + 2) * c->N;  // particle slots, prototypes, the shared empty row
+  // engine: the copy-on-write pool unless PMDI_ENGINE=dense asks for the dense form (every particle owns its
+  // N rows); particle sharding over several GPUs runs on the dense engine
+  const char* eng = getenv("PMDI_ENGINE");
+  c->engine = (eng && std::string(eng) == "dense") ? 0 : 1;
+  if (c->R > 1 && !(eng && std::string(eng) == "pool")) c->engine = 0;
+  if (getenv("PMDI_WATCHDOG_S")) c->wd_ns = (unsigned long long)(atof(getenv("PMDI_WATCHDOG_S")) * 1e9);
+  // dense: particle slots, prototypes, the shared empty row.  pool: at most Ps*N live rows, one reservation per
+  // chosen row in flight (<= Ps per dataset), the N prefix rows, the empty cluster
+  const long long rows = c->engine ? (long long)c->Ps * c->N + c->Ps + c->N + 2 : (long long)(c->Ps + 2) * c->N;
+  if (rows > 0x7fffff00ll) return fail(1, "pmdi: particles x N too large");
   const int Gmax = std::min(c->n_sm, c->Ps);
   size_t off_b = 0;
   auto take = [&](size_t bytes) { const size_t o = off_b; off_b = (off_b + bytes + 255) / 256 * 256; return o; };
@@ -228,7 +256,8 @@ int build_layout(pmdi_ctx* c) {
   const size_t o_ess = take(sizeof(double) * 6 * (size_t)c->R * Gmax);
   const size_t o_lw = take(sizeof(double) * (size_t)c->P);
   const size_t o_log = take((size_t)c->n * K * c->P);  // at most n_obs observation steps
-  struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n; };
+  const size_t o_rankp = take(sizeof(double) * 2 * 8 * 4);
+  struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n, cw, refcnt, chosen, dst, neval, live, free_, rowmap, ctr; };
   std::vector<Off> offs(K);
   for (int k = 0; k < K; ++k) {
     Dataset& s = c->ds[k];
@@ -238,11 +267,22 @@ int build_layout(pmdi_ctx* c) {
       o.mu = take(8 * rows * s.Dp); o.lamn = take(8 * rows * s.Dp);
       o.sum = take(8 * rows * s.Dp); o.beta = take(8 * rows * s.Dp);
     } else if (s.type == T_CATEGORICAL) {
-      o.cnt = take(4 * rows * (size_t)s.Lmax * s.Dp);
+      if (c->engine) {
+        s.fpw = c->n < 65536 ? 4 : 2;  // count fields per 64-bit word: 16 bits hold any count when n_obs < 65536
+        s.wpf = (s.Lmax + s.fpw - 1) / s.fpw;
+        o.cw = take(8 * rows * (size_t)s.Dp * s.wpf);
+      } else {
+        o.cnt = take(4 * rows * (size_t)s.Lmax * s.Dp);
+      }
     } else {
       o.S = take(8 * rows * s.Dp);
     }
     o.part = take(8 * rows * s.J); o.aux = take(8 * rows * s.J); o.n = take(4 * rows);
+    if (c->engine) {
+      s.cap = (int)rows;
+      o.refcnt = take(4 * rows); o.chosen = take(8 * rows); o.dst = take(8 * rows); o.neval = take(4 * rows);
+      o.live = take(4 * rows); o.free_ = take(4 * rows); o.rowmap = take(8 * (size_t)c->Ps * c->N); o.ctr = take(64);
+    }
   }
   if (c->arena) { cudaFree(c->arena); c->arena = nullptr; }
   CK(cudaMalloc((void**)&c->arena, off_b));
@@ -253,21 +293,30 @@ int build_layout(pmdi_ctx* c) {
   c->ess_part.view(A + o_ess, 6 * (size_t)c->R * Gmax);
   c->lw.view(A + o_lw, c->P);
   c->alloc_log.view(A + o_log, (size_t)c->n * K * c->P);
+  c->rank_part.view(A + o_rankp, 2 * 8 * 4);
   for (int k = 0; k < K; ++k) {
     Dataset& s = c->ds[k];
     const Off& o = offs[k];
+    if (c->engine) {
+      if (s.type == T_CATEGORICAL) s.cw.view(A + o.cw, rows * (size_t)s.Dp * s.wpf);
+      s.p_refcnt.view(A + o.refcnt, rows); s.p_chosen.view(A + o.chosen, 2 * rows); s.p_dst.view(A + o.dst, 2 * rows);
+      s.p_neval.view(A + o.neval, rows); s.p_live.view(A + o.live, rows); s.p_free.view(A + o.free_, rows);
+      s.p_rowmap.view(A + o.rowmap, 2 * (size_t)c->Ps * c->N); s.p_ctr.view(A + o.ctr, 16);
+    }
     if (s.type == T_GAUSSIAN) {
       s.mu.view(A + o.mu, rows * s.Dp); s.lamn.view(A + o.lamn, rows * s.Dp);
       s.sum.view(A + o.sum, rows * s.Dp); s.beta.view(A + o.beta, rows * s.Dp);
     } else if (s.type == T_CATEGORICAL) {
-      s.cnt.view(A + o.cnt, rows * (size_t)s.Lmax * s.Dp);
+      if (!c->engine) s.cnt.view(A + o.cnt, rows * (size_t)s.Lmax * s.Dp);
     } else {
       s.S.view(A + o.S, rows * s.Dp);
     }
     s.part.view(A + o.part, rows * s.J); s.aux.view(A + o.aux, rows * s.J); s.n.view(A + o.n, rows);
     DsDev d;
     fill_dsdev(c, k, d);
-    k_init_rows<<<c->n_sm * 4, 256, 0, c->stream>>>(d, rows);
+    if (!(c->engine && s.type == T_CATEGORICAL)) k_init_rows<<<c->n_sm * 4, 256, 0, c->stream>>>(d, rows);
+    else {  // the arena is zeroed: packed counts, aux, part and n of every row start empty
+    }
     CK(cudaGetLastError());
   }
   CK(cudaStreamSynchronize(c->stream));
@@ -295,26 +344,47 @@ int assign_units(pmdi_ctx* c) {
   }
   c->cta_off[G] = (int)c->cta_units.size();
   c->max_units = max_slots * K;
-  // dynamic shared memory: 4 observation buffers | lf | proposal scratch | Pi | lw | inc | part x2 |
-  // items x2 | unit tables
   const int Npad = (N + 31) & ~31;
   int dev_smem = 0;
   CK(cudaDeviceGetAttribute(&dev_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->device));
   const long long MU = c->max_units, MS = max_slots;
-  const long long fixed = 4LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 +
-                          MS * 8 + 2 * MU * 8 + MU * N * 4 + (12 * MU + 2 * MS) * 4 + 64;
-  const long long avail = (long long)dev_smem - 6144 - fixed;
-  const long long want_items = MU * N * c->Jmax;  // every label of every unit occupied
-  if (avail < 24LL * MU * c->Jmax * 2)
-    return fail(4, "pmdi: datasets too wide / too many particles per SM for the shared-memory work queue");
-  long long items_b = std::min(want_items * 24, avail / 2);
-  const long long lf_b = std::min<long long>((long long)c->lf_want * 8, avail - items_b);
-  items_b = std::min(want_items * 24, avail - lf_b);
-  c->item_cap = (int)(items_b / 24);
-  c->lf_T = (int)(lf_b / 8);
-  if (c->lf_want > 0 && c->lf_T < 256) return fail(4, "pmdi: no shared memory left for the log-factorial table");
-  c->dyn_smem = (size_t)fixed + (size_t)c->lf_T * 8 + (size_t)c->item_cap * 24;
-  CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+  if (c->engine) {
+    // pool engine: observation ring (2..4 deep) | lf | proposal scratch | Pi | lw | inc | unit tables
+    const long long tables = (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 + MS * 8 + MU * 8 +
+                             (MU * 10 + MS + MU * N) * 4 + 64;
+    const long long budget = (long long)dev_smem - 4096 - tables;
+    int ring = PMDI_OBS_RING;
+    while (ring > 2 && (long long)ring * c->sm_x_bytes + std::min<long long>((long long)c->lf_want * 8, 64 * 1024) > budget) --ring;
+    if ((long long)ring * c->sm_x_bytes + (c->lf_want > 0 ? 2048 : 0) > budget)
+      return fail(4, "pmdi: one observation over all datasets is " + std::to_string(c->sm_x_bytes) +
+                         " bytes; two of them must fit in shared memory (" + std::to_string(budget / 2) +
+                         " bytes each with this N and particle count)");
+    c->obs_ring = ring;
+    const long long lf_b = std::min<long long>((long long)c->lf_want * 8, budget - (long long)ring * c->sm_x_bytes);
+    c->lf_T = (int)(lf_b / 8);
+    c->item_cap = 0;
+    c->dyn_smem = (size_t)((long long)ring * c->sm_x_bytes + (long long)c->lf_T * 8 + tables);
+    CK(cudaFuncSetAttribute(k_sweep_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+  } else {
+    // dense engine: 4 observation buffers | lf | proposal scratch | Pi | lw | inc | part x2 | items x2 | unit tables
+    const long long fixed = 4LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 +
+                            MS * 8 + 2 * MU * 8 + MU * N * 4 + (12 * MU + 2 * MS) * 4 + 64;
+    const long long avail = (long long)dev_smem - 6144 - fixed;
+    const long long want_items = MU * N * c->Jmax;  // every label of every unit occupied
+    if (avail < 24LL * MU * c->Jmax * 2)
+      return fail(4, "pmdi: datasets too wide / too many particles per SM for the shared-memory work queue of the "
+                     "dense engine (4 x " + std::to_string(c->sm_x_bytes) + " bytes of staged observations)");
+    long long items_b = std::min(want_items * 24, avail / 2);
+    const long long lf_b = std::min<long long>((long long)c->lf_want * 8, avail - items_b);
+    items_b = std::min(want_items * 24, avail - lf_b);
+    c->item_cap = (int)(items_b / 24);
+    c->lf_T = (int)(lf_b / 8);
+    if (c->lf_want > 0 && c->lf_T < 256) return fail(4, "pmdi: no shared memory left for the log-factorial table");
+    c->dyn_smem = (size_t)fixed + (size_t)c->lf_T * 8 + (size_t)c->item_cap * 24;
+    CK(cudaFuncSetAttribute(k_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+  }
+  if (c->sm_x_bytes > 48 * 1024)
+    CK(cudaFuncSetAttribute(k_empty_lp, cudaFuncAttributeMaxDynamicSharedMemorySize, c->sm_x_bytes));
   CK(c->d_cta_off.ensure(c->cta_off.size()));
   CK(c->d_cta_units.ensure(c->cta_units.size()));
   CK(cudaMemcpyAsync(c->d_cta_off.p, c->cta_off.data(), sizeof(int) * c->cta_off.size(), cudaMemcpyHostToDevice, c->stream));
@@ -333,6 +403,10 @@ int fill_params(pmdi_ctx* c) {
     sp.ds[k].x_off = off;
     off += c->ds[k].Dp * (c->ds[k].type == T_GAUSSIAN ? 8 : 4);
   }
+  for (int k = 0; k < c->K; ++k) fill_pooldev(c, k, sp.pd[k]);
+  sp.engine = c->engine; sp.obs_ring = c->obs_ring; sp.wd_ns = c->wd_ns;
+  sp.proto_base = c->engine ? 0 : (long long)c->Ps * c->N;
+  sp.rank_part = c->rank_part.p;
   sp.K = c->K; sp.N = c->N; sp.P = c->P; sp.n_obs = (int)c->n; sp.G = c->G;
   sp.R = c->R; sp.rank = c->rank; sp.Ps = c->Ps; sp.slot0 = c->rank * c->Ps;
   for (int r = 0; r < 8; ++r) sp.peer_delta[r] = c->peer_delta[r];
@@ -344,6 +418,7 @@ int fill_params(pmdi_ctx* c) {
   // warps have work (cfg2, 6 units: 1-2 blocks best, 3 already +3 %); with many units a whole row per item
   // is best (cfg4, 14 units: 8 blocks 9 % faster than 2) - profiles/r01_k_sweep_cfg4.md.  PMDI_QB overrides.
   sp.qb = getenv("PMDI_QB") ? std::max(1, atoi(getenv("PMDI_QB"))) : (c->max_units >= 11 ? std::max(2, c->Jmax) : 2);
+  if (c->engine) sp.qb = getenv("PMDI_QB") ? std::max(1, atoi(getenv("PMDI_QB"))) : 0;  // pool: 0 = chosen per step
   return 0;
 }
 
@@ -642,10 +717,12 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   CK(c->sc_w.ensure(P)); CK(c->sc_pp.ensure(P)); CK(c->sc_u.ensure(P));
   CK(c->sc_j.ensure(P)); CK(c->sc_anc0.ensure(P)); CK(c->sc_a.ensure(P)); CK(c->sc_b.ensure(P));
   CK(c->sc_c.ensure(P)); CK(c->sc_d.ensure(P)); CK(c->copies.ensure(P)); CK(c->plan_out.ensure(4));
-  CK(c->err.ensure(4)); CK(c->rows_eval.ensure(PMDI_MAX_K)); CK(c->counters.ensure(4));
+  CK(c->err.ensure(4)); CK(c->rows_eval.ensure(PMDI_MAX_K)); CK(c->counters.ensure(8));
   CK(c->phase_ns.ensure(8 * (size_t)c->G)); CK(c->d_pstar.ensure(1)); CK(c->cluster_n.ensure((size_t)K * P * N));
   CK(c->members.ensure((size_t)K * std::max<long long>(a->n1 - 1, 1))); CK(c->mem_off.ensure((size_t)K * (N + 1)));
   CK(c->cur_at.ensure(steps));
+  CK(c->rows_ref.ensure(PMDI_MAX_K)); CK(c->label_counts.ensure((size_t)N * K)); CK(c->pair_agree.ensure(std::max(npairs, 1)));
+  sp.rows_ref = c->rows_ref.p;
   sp.n1 = (int)a->n1; sp.steps = steps; sp.flags = (int)a->flags;
   sp.Pi = c->Pi.p; sp.l1phi = c->l1phi.p; sp.s_in = c->s_in.p; sp.order = c->order.p;
   sp.lw_init = a->logweight_init; sp.seed = a->seed; sp.iter = a->iter;
@@ -708,15 +785,22 @@ int pmdi_sweep_run(pmdi_ctx* c) {
   for (int k = 0; k < K; ++k) maxDp = std::max(maxDp, c->ds[k].Dp);
   k_prefix_build<<<dim3((maxDp + 127) / 128, N, K), 128, 0, st>>>(sp, c->members.p, c->mem_off.p);
   k_proto_aux<<<dim3(N, K), 256, 0, st>>>(sp);
-  k_broadcast<<<c->n_sm * 8, 256, 0, st>>>(sp);
-  k_empty_lp<<<sp.steps, 256, c->sm_x_bytes, st>>>(sp, c->lp_empty.p);
-  CK(cudaGetLastError());
-  CK(cudaEventRecord(c->ev1, st));
   void* args[] = {(void*)&c->sp};
-  CK(cudaLaunchCooperativeKernel((const void*)k_sweep, dim3(c->G), dim3(PMDI_NT), args, c->dyn_smem, st));
+  if (c->engine) {
+    k_pool_init<<<K, 1024, 0, st>>>(sp);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaLaunchCooperativeKernel((const void*)k_sweep_pool, dim3(c->G), dim3(PMDI_NT), args, c->dyn_smem, st));
+  } else {
+    k_broadcast<<<c->n_sm * 8, 256, 0, st>>>(sp);
+    k_empty_lp<<<sp.steps, 256, c->sm_x_bytes, st>>>(sp, c->lp_empty.p);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, st));
+    CK(cudaLaunchCooperativeKernel((const void*)k_sweep, dim3(c->G), dim3(PMDI_NT), args, c->dyn_smem, st));
+  }
   CK(cudaEventRecord(c->ev2, st));
-  k_finish<<<1, 256, 0, st>>>(sp, (c->sweep_flags & PMDI_SWEEP_SSTAR_COMPAT) ? 1 : 0, c->s_out.p, c->d_pstar.p,
-                              c->cluster_n.p, c->cur_at.p);
+  k_finish_pool<<<1, 256, 0, st>>>(sp, (c->sweep_flags & PMDI_SWEEP_SSTAR_COMPAT) ? 1 : 0, c->s_out.p, c->d_pstar.p,
+                                   c->cluster_n.p, c->cur_at.p, c->label_counts.p, c->pair_agree.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev3, st));
   c->ran = true;
@@ -731,13 +815,18 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   const long long n = c->n;
   const int steps = c->sp.steps;
   int err = 0;
-  long long counters[4] = {0, 0, 0, 0};
-  unsigned long long rows[PMDI_MAX_K];
+  long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned long long rows[PMDI_MAX_K], rref[PMDI_MAX_K];
   std::vector<unsigned long long> phase(8 * (size_t)c->G, 0ull);
   long long pstar = 0;
   CK(cudaMemcpyAsync(&err, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(counters, c->counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(rows, c->rows_eval.p, sizeof(rows), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(rref, c->rows_ref.p, sizeof(rref), cudaMemcpyDeviceToHost, st));
+  if (o->label_counts)
+    CK(cudaMemcpyAsync(o->label_counts, c->label_counts.p, sizeof(int64_t) * N * K, cudaMemcpyDeviceToHost, st));
+  if (o->pair_agree && K > 1)
+    CK(cudaMemcpyAsync(o->pair_agree, c->pair_agree.p, sizeof(int64_t) * (K * (K - 1) / 2), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(phase.data(), c->phase_ns.p, 8 * sizeof(unsigned long long) * c->G, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&pstar, c->d_pstar.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
   if (o->s) CK(cudaMemcpyAsync(o->s, c->s_out.p, sizeof(int64_t) * n * K, cudaMemcpyDeviceToHost, st));
@@ -778,19 +867,26 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
     return fail(50 + err, err == 77 ? "pmdi_sweep: grid barrier watchdog fired (a CTA did not arrive)"
                           : err == 79 ? "pmdi_sweep: work-queue watchdog fired (a warp waited 4 s for work)"
                           : err == 78 ? "pmdi_sweep: shared-memory work queue overflow (too many occupied clusters per SM)"
+                          : err == 80 ? "pmdi_sweep: cluster pool exhausted"
                                     : "pmdi_sweep: device-side error " + std::to_string(err));
   if (o->p_star) *o->p_star = pstar;
   o->n_resamples = counters[0];
   o->n_copies = counters[1];
   o->n_remote_rows = counters[3];
+  o->rows_evaluated_ahead = counters[4];
   long long ev = 0, dense = 0;
   for (int k = 0; k < K; ++k) {
-    rows[k] += (unsigned long long)steps;  // the shared empty cluster: one evaluation per step
+    if (!c->engine) {
+      rref[k] = rows[k];                     // dense engine: every referenced row is evaluated
+      rows[k] += (unsigned long long)steps;  // the shared empty cluster: one evaluation per step
+    }
     ev += (long long)rows[k] * c->ds[k].D;
     dense += (long long)steps * P * N * c->ds[k].D;
     o->rows_evaluated[k] = (int64_t)rows[k];
+    o->rows_referenced[k] = (int64_t)rref[k];
   }
-  for (int k = K; k < 8; ++k) o->rows_evaluated[k] = 0;
+  for (int k = K; k < 8; ++k) { o->rows_evaluated[k] = 0; o->rows_referenced[k] = 0; }
+  o->engine = c->engine;
   o->n_evals = ev;
   o->n_evals_dense = dense;
   float ms = 0.f;
@@ -914,6 +1010,8 @@ int pmdi_cluster_eval(pmdi_ctx* c, int32_t k, const int64_t* rows, int64_t m, in
     CK(c->scratch_d.ensure(8));
     k_build_one<<<(s.Dp + 127) / 128, 128, 0, st>>>(c->sp, k, c->members.p, (int)m);
     k_aux_one<<<1, 256, 0, st>>>(c->sp, k);
+    if (s.Dp * 8 > 48 * 1024)
+      CK(cudaFuncSetAttribute(k_eval_row, cudaFuncAttributeMaxDynamicSharedMemorySize, s.Dp * 8));
     k_eval_row<<<1, 32, s.Dp * 8, st>>>(c->sp, k, (int)(obs - 1), c->scratch_d.p);
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out_logprob, c->scratch_d.p, sizeof(double), cudaMemcpyDeviceToHost, st));

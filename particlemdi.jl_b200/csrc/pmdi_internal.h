@@ -41,6 +41,29 @@ struct DsDev {
   int* n;
 };
 
+/*
+ * Pool engine (pool_kernel.cuh): the reference's copy-on-write cluster pool (src/pmdi.jl:131-146,
+ * 275-310) on the device.  A dataset's statistics rows are a POOL of `cap` physical rows; a particle
+ * refers to its clusters through rowmap[slot][label] -> row.  Particles that have made the same
+ * choices share rows; a row is evaluated once per observation whatever the number of particles that
+ * refer to it, and resampling permutes row maps instead of moving statistics.  Row cap-1 is the
+ * EMPTY cluster (never written; every unoccupied label of every particle refers to it).
+ */
+struct PoolDev {
+  int cap;           /* physical rows, row cap-1 = the empty cluster                         */
+  int wpf, fpw;      /* categorical packing: 64-bit words per feature, count fields per word  */
+  int pad;
+  int* refcnt;       /* [cap] (particle, label) references of a row                          */
+  int* chosen;       /* [2][cap] by step parity: particles that chose the row this step       */
+  int* dst;          /* [2][cap] by step parity: row id reserved for the split of the row     */
+  int* n_eval;       /* [cap] cluster size the row's current predictive was evaluated with    */
+  int* live;         /* [cap] list of live rows (live[0] = the empty cluster)                 */
+  int* freelist;     /* [cap] stack of free rows                                              */
+  int* rowmap;       /* [2][Ps][N] by resampling-event parity: label -> row of a particle slot */
+  int* ctr;          /* [0] live rows, [1] free rows                                          */
+  unsigned long long* cw; /* [cap][Dp][wpf] packed categorical counts                          */
+};
+
 struct SweepParams {
   int K, N, P, n_obs, n1, steps;
   int G, flags;
@@ -49,6 +72,13 @@ struct SweepParams {
   int R, rank, Ps, slot0;
   long long peer_delta[8];
   DsDev ds[PMDI_MAX_K];
+  PoolDev pd[PMDI_MAX_K];
+  int engine;             /* 0 dense (sweep_kernel.cuh), 1 pool (pool_kernel.cuh)            */
+  int obs_ring;           /* depth of the shared-memory observation ring (2..4)              */
+  long long proto_base;   /* first row of the rho-prefix prototypes (dense: Ps*N, pool: 0)   */
+  unsigned long long wd_ns; /* watchdog of the in-kernel waits                               */
+  double* rank_part;      /* [2][R][4] per step parity and rank: max, sum w, sum w^2, step tag */
+  unsigned long long* rows_ref; /* [K] occupied (particle, label) rows referenced by proposals */
   const double* Pi;      /* [K][N]                                          */
   const double* l1phi;   /* [npairs] log(1+phi)                             */
   const long long* s_in; /* [K][n_obs] labels 1..N                          */

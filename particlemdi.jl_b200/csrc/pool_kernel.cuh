@@ -1,0 +1,845 @@
+// The conditional-SMC sweep over a COPY-ON-WRITE CLUSTER POOL: the per-observation loop of the
+// reference (src/pmdi.jl:209-342) as one persistent cooperative kernel in which
+//   * a cluster shared by several particles is ONE physical row, evaluated once per observation
+//     (the reference's `for id in 1:maximum(particle_k)` loop, src/pmdi.jl:218-220);
+//   * cluster_add! is copy-on-write (src/pmdi.jl:275-310): when every particle that refers to a row
+//     chose it the row is updated in place, otherwise the choosers get a fresh row (one per source
+//     row, shared by all of them) and the others keep the old one;
+//   * resampling (src/pmdi.jl:318-341) permutes the particles' row maps and recounts references -
+//     no statistics move.
+// Same results as the dense form (every particle owning its N clusters): a row's content and its
+// predictive do not depend on how many particles share it.
+//
+// Per observation step t the grid runs two phases separated by grid barriers:
+//   E(t)  every live row's predictive of x[t]  (warps take (row, feature-block) items round-robin
+//         over the whole grid).  A row that was chosen at step t-1 gets x[t-1] added in the same
+//         pass: in place, or - split - source row read once, fresh row written, both evaluated.
+//   -- B1 --
+//   P(t)  per (dataset, particle) unit, one warp: gather the lp of the particle's N labels through
+//         its row map, softmax-cdf, draw, weight increment (src/pmdi.jl:223-265); count the
+//         choosers of the chosen row; the first chooser reserves a row for a possible split.  The
+//         K-th proposal of a particle folds its log-weight with the Phi coupling (src/misc.jl:50-59);
+//         the CTA's last particle publishes the CTA's (max, sum w, sum w^2).
+//   -- B2 --
+//   R(t)  choosers learn the row their label now maps to (tot == refcnt: in place); one warp per
+//         CTA evaluates calc_ESS (src/misc.jl:15-25) - then straight into E(t+1).
+// The ESS decision of step t is needed only before P(t+1): evaluations never depend on it (rows
+// do not change under resampling), so with several GPUs the cross-rank exchange of the ESS
+// partials is off the dependent chain; it has the whole of E(t+1) to arrive.
+#pragma once
+#include "pool_types.cuh"
+#include "sweep_kernel.cuh"
+
+#define POOL_BIG_REF (1 << 30)
+
+struct PoolSmem {
+  unsigned long long obs_bar[PMDI_OBS_RING];
+  unsigned long long epoch;    // local grid-barrier arrivals expected so far
+  double res_mx;
+  int res_flag;                // the last resolved step resamples
+  int fail;
+  int ev;                      // resampling events so far
+  int pdone;                   // particles of this CTA folded this step
+  int U[2][PMDI_MAX_K];        // by step parity: live rows covered by the step's item list
+  int qb[2][PMDI_MAX_K];       // by step parity: 256-feature blocks per item
+  int ibase[2][PMDI_MAX_K + 1];  // by step parity: first item of each dataset
+  unsigned rows_eval[PMDI_MAX_K], rows_ref[PMDI_MAX_K];
+  unsigned long long tacc[8];
+};
+
+struct PoolTables {
+  double* lf;      // [lf_T]
+  double* lp_s;    // [NW][Npad]
+  double* Pi_s;    // [K][N]
+  double* lw_s;    // [MS]
+  double* inc_s;   // [MS*K]
+  int* lab_s;      // [MS*K]
+  int* pcount;     // [MS]
+  int* u_c;        // [MU] row chosen by the unit this step
+  int* u_lab;      // [MU] label chosen
+  int* u_lead;     // [MU] first chooser of the row
+  int* u_duty;     // [MU] deferred bookkeeping of a leader: 0 none, 1 in place, 2 split
+  int* u_dc;       // [MU] duty: source row
+  int* u_dd;       // [MU] duty: destination row
+  int* u_dtot;     // [MU] duty: number of choosers
+  int* u_spare;    // [MU] row reserved by the unit for the next split it leads
+  int* rm_s;       // [MU][N] the units' row maps (copy of rowmap[ev & 1] rows of the owned slots)
+};
+
+// local grid barrier (this GPU's CTAs), all threads
+__device__ __noinline__ bool pool_gsync(const SweepParams& sp, PoolSmem& sm) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    sm.epoch += (unsigned long long)sp.G;
+    __threadfence();
+    atomicAdd((unsigned long long*)sp.bar, 1ull);
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_u64((const unsigned long long*)sp.bar) < sm.epoch) {
+      if (((++spins) & 0x3ffu) == 0) {
+        if (__ldcg(sp.err) != 0) { sm.fail = 1; break; }
+        if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); sm.fail = 1; break; }
+      }
+    }
+    __threadfence();
+    if (__ldcg(sp.err) != 0) sm.fail = 1;  // every CTA leaves at the same barrier
+  }
+  __syncthreads();
+  return sm.fail == 0;
+}
+
+// one thread: bulk-copy the K rows of the observation swept at `step` into its ring slot
+__device__ __noinline__ void pool_issue_obs(const SweepParams& sp, int step, unsigned char* xring,
+                                            unsigned long long* bars) {
+  if (step >= sp.steps) return;
+  const int b = step % sp.obs_ring;
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(bars + b);
+  const int obs = sp.order[sp.n1 - 1 + step];
+  unsigned total = 0;
+#pragma unroll 1
+  for (int k = 0; k < sp.K; ++k) total += (unsigned)sp.ds[k].Dp * (sp.ds[k].type == T_GAUSSIAN ? 8u : 4u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the slot
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
+#pragma unroll 1
+  for (int k = 0; k < sp.K; ++k) {
+    const DsDev& ds = sp.ds[k];
+    const unsigned bytes = (unsigned)ds.Dp * (ds.type == T_GAUSSIAN ? 8u : 4u);
+    const unsigned char* src = (const unsigned char*)ds.xstage + (size_t)obs * bytes;
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(xring + (size_t)b * sp.sm_x_bytes + ds.x_off);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+  }
+}
+
+// item list of the E phase of step `st` (parity b): live-row counts as they are now (stable during
+// the P phase before it), blocks per item so that the grid's warps all get work.  One thread.
+__device__ __noinline__ void pool_snapshot(const SweepParams& sp, PoolSmem& sm, int b) {
+  const int GW = sp.G * (PMDI_NT / 32);
+  long long W = 0;
+  for (int k = 0; k < sp.K; ++k) { sm.U[b][k] = ldcg_i32(sp.pd[k].ctr); W += sm.U[b][k]; }
+  const int f = (int)max(1ll, min((long long)sp.Jmax, (long long)GW / max(W, 1ll)));
+  int base = 0;
+  for (int k = 0; k < sp.K; ++k) {
+    const int J = sp.ds[k].J;
+    const int pieces = min(J, f);
+    const int qb = sp.qb > 0 ? min(J, sp.qb) : (J + pieces - 1) / pieces;
+    sm.qb[b][k] = qb;
+    sm.ibase[b][k] = base;
+    base += sm.U[b][k] * ((J + qb - 1) / qb);
+  }
+  sm.ibase[b][sp.K] = base;
+}
+
+// plain predictive of blocks [j0, j1) of row r (no pending add)
+__device__ __forceinline__ double pool_eval_plain(const SweepParams& sp, int k, long long r, int j0, int j1, int n,
+                                                  const unsigned char* xs, const double* lf, int lane) {
+  const DsDev& ds = sp.ds[k];
+  const int base = j0 * PMDI_FB + 2 * lane;
+  const int nits = (min(ds.Dp, j1 * PMDI_FB) - j0 * PMDI_FB) / PMDI_WF;
+  if (ds.type == T_GAUSSIAN)
+    return gauss_eval_raw(ds.mu + r * ds.Dp + base, ds.lamn + r * ds.Dp + base, ds.aux + r * ds.J + j0,
+                          ds.all_on ? nullptr : ds.flag + base,
+                          (unsigned)__cvta_generic_to_shared(xs + ds.x_off) + base * 8u, nits, j1 - j0, n, lane);
+  if (ds.type == T_NEGBINOM)
+    return nb_eval_raw(ds.S + r * ds.Dp + base, ds.aux + r * ds.J + j0,
+                       (unsigned)__cvta_generic_to_shared(xs + ds.x_off) + base * 4u, nits, j1 - j0, n,
+                       (unsigned)__cvta_generic_to_shared(lf), sp.lf_T, lane);
+  const PoolDev& pd = sp.pd[k];
+  return cat_eval_pool(pd.cw + ((size_t)r * ds.Dp + base) * pd.wpf, pd.wpf, pd.fpw,
+                       (unsigned)__cvta_generic_to_shared(xs + ds.x_off) + base * 4u, nits);
+}
+
+// cluster_add!(x_prev) src -> dst of blocks [j0, j1) + predictive of x_cur; n = size after the add.
+// Returns the updated row's partial; with SPLIT, *v_src = the source row's partial.
+template <bool SPLIT>
+__device__ __forceinline__ double pool_eval_cow(const SweepParams& sp, int k, long long src, long long dst, int j0,
+                                                int j1, int n, const unsigned char* xp, const unsigned char* xc,
+                                                const double* lf, int lane, double* v_src) {
+  const DsDev& ds = sp.ds[k];
+  double vd = 0.0, vs = 0.0;
+#pragma unroll 1
+  for (int j = j0; j < j1; ++j) {
+    const int q0 = j * PMDI_FB;
+    const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+    const int base = q0 + 2 * lane;
+    double es = 0.0;
+    if (ds.type == T_GAUSSIAN) {
+      const long long so = src * ds.Dp + base, dof = dst * ds.Dp + base;
+      vd += gauss_cow_block<SPLIT>(ds.sum + so, ds.beta + so, ds.mu + so, ds.lamn + so, ds.sum + dof,
+                                   ds.beta + dof, ds.mu + dof, ds.lamn + dof, ds.aux + dst * ds.J + j,
+                                   ds.flag + base, nit, n, (const double*)(xp + ds.x_off) + base,
+                                   (const double*)(xc + ds.x_off) + base, &es);
+      if (SPLIT) vs += ldcg_f64(ds.aux + src * ds.J + j) - (0.5 * (double)(n - 1) + 1.0) * es;
+    } else if (ds.type == T_NEGBINOM) {
+      vd += nb_cow_block<SPLIT>(ds.S + src * ds.Dp + base, ds.S + dst * ds.Dp + base, ds.aux + dst * ds.J + j, nit, n,
+                                (unsigned)__cvta_generic_to_shared(xp + ds.x_off) + base * 4u,
+                                (unsigned)__cvta_generic_to_shared(xc + ds.x_off) + base * 4u,
+                                (unsigned)__cvta_generic_to_shared(lf), sp.lf_T, &es);
+      if (SPLIT) vs += ldcg_f64(ds.aux + src * ds.J + j) + es;
+    } else {
+      const PoolDev& pd = sp.pd[k];
+      vd += cat_cow_block<SPLIT>(pd.cw + ((size_t)src * ds.Dp + base) * pd.wpf,
+                                 pd.cw + ((size_t)dst * ds.Dp + base) * pd.wpf, pd.wpf, pd.fpw, nit,
+                                 (unsigned)__cvta_generic_to_shared(xp + ds.x_off) + base * 4u,
+                                 (unsigned)__cvta_generic_to_shared(xc + ds.x_off) + base * 4u, &es);
+      if (SPLIT) vs += es;
+    }
+  }
+  if (SPLIT) *v_src = vs;
+  return vd;
+}
+
+// E phase of step `st`: predictive of x[st] for every live row; rows chosen at step st-1 (pending
+// parity pp = (st-1)&1, or -1 at the first step) get x[st-1] added on the way.
+__device__ __noinline__ void pool_eval_phase(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int st, int pp,
+                                             unsigned char* xring, int& obs_ok) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = PMDI_NT / 32;
+  const int b = st & 1, K = sp.K;
+  const int GW = sp.G * NW, gw = warp * sp.G + (int)blockIdx.x;
+  const int total = sm.ibase[b][K];
+  const unsigned char* xc = xring + (size_t)(st % sp.obs_ring) * sp.sm_x_bytes;
+  const unsigned char* xp = xring + (size_t)((st + sp.obs_ring - 1) % sp.obs_ring) * sp.sm_x_bytes;
+#pragma unroll 1
+  for (int idx = gw; idx < total; idx += GW) {
+    if (obs_ok < st) {  // x[st] has landed in the ring (x[st-1] was waited for one step ago)
+      if (lane == 0) {
+#pragma unroll 1
+        for (int s = max(obs_ok + 1, st - 1); s <= st; ++s)
+          while (!mbar_try_wait(&sm.obs_bar[s % sp.obs_ring], (unsigned)(s / sp.obs_ring) & 1u)) {}
+      }
+      __syncwarp();
+      obs_ok = st;
+    }
+    int k = 0;
+#pragma unroll 1
+    while (k + 1 < K && idx >= sm.ibase[b][k + 1]) ++k;
+    const DsDev& ds = sp.ds[k];
+    const PoolDev& pd = sp.pd[k];
+    const int qb = sm.qb[b][k], JQ = (ds.J + qb - 1) / qb;
+    const int rel = idx - sm.ibase[b][k];
+    const int li = rel / JQ, q = rel - li * JQ;
+    const int j0 = q * qb, j1 = min(ds.J, j0 + qb);
+    const int c = ldcg_i32(pd.live + li);
+    const int tot = pp >= 0 ? ldcg_i32(pd.chosen + (size_t)pp * pd.cap + c) : 0;
+    const int nc = ldcg_i32(ds.n + c);
+    if (tot == 0) {
+      double v = pool_eval_plain(sp, k, c, j0, j1, nc, xc, T.lf, lane);
+      if (lane == 0) {
+        if (q == 0) { v = __ldg(ds.rc + nc) + v; atomicAdd(&sm.rows_eval[k], 1u); }  // rc first: the order of the sum
+        __stcg(ds.part + (long long)c * ds.J + j0, v);
+      }
+    } else if (tot == ldcg_i32(pd.refcnt + c)) {  // every reference chose it: in place (src/pmdi.jl:284-286)
+      double dummy;
+      double v = pool_eval_cow<false>(sp, k, c, c, j0, j1, nc + 1, xp, xc, T.lf, lane, &dummy);
+      if (lane == 0) {
+        if (q == 0) { v = __ldg(ds.rc + nc + 1) + v; atomicAdd(&sm.rows_eval[k], 1u); }
+        __stcg(ds.part + (long long)c * ds.J + j0, v);
+      }
+    } else {  // split: the choosers' copy goes to row d, the others keep c (src/pmdi.jl:288-309)
+      const int d = ldcg_i32(pd.dst + (size_t)pp * pd.cap + c);
+      double vs;
+      double vd = pool_eval_cow<true>(sp, k, c, d, j0, j1, nc + 1, xp, xc, T.lf, lane, &vs);
+      if (lane == 0) {
+        if (q == 0) {
+          vs = __ldg(ds.rc + nc) + vs;
+          vd = __ldg(ds.rc + nc + 1) + vd;
+          atomicAdd(&sm.rows_eval[k], 2u);
+        }
+        __stcg(ds.part + (long long)c * ds.J + j0, vs);
+        __stcg(ds.part + (long long)d * ds.J + j0, vd);
+      }
+    }
+  }
+}
+
+// Deferred bookkeeping of the rows this CTA's leaders resolved at the previous step: after the
+// barrier that follows R, nobody reads the old counts any more.  Thread per unit.
+__device__ __forceinline__ void pool_duties(const SweepParams& sp, const PoolTables& T, int nu, int pp) {
+  for (int u = threadIdx.x; u < nu; u += PMDI_NT) {
+    const int duty = T.u_duty[u];
+    if (!duty) continue;
+    const int k = u % sp.K;
+    const PoolDev& pd = sp.pd[k];
+    const int c = T.u_dc[u], d = T.u_dd[u], tot = T.u_dtot[u];
+    __stcg(pd.chosen + (size_t)pp * pd.cap + c, 0);
+    if (duty == 1) {
+      __stcg(sp.ds[k].n + c, ldcg_i32(sp.ds[k].n + c) + 1);
+    } else {
+      if (c != pd.cap - 1) __stcg(pd.refcnt + c, ldcg_i32(pd.refcnt + c) - tot);
+      __stcg(pd.refcnt + d, tot);
+    }
+    T.u_duty[u] = 0;
+  }
+}
+
+// R phase for this CTA's units: the row each chooser's label maps to from now on.  Thread per unit.
+__device__ __forceinline__ void pool_resolve_units(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int nu,
+                                                   int par) {
+  const int K = sp.K, N = sp.N, G = sp.G;
+  for (int u = threadIdx.x; u < nu; u += PMDI_NT) {
+    const int k = u % K, slot = (int)blockIdx.x + (u / K) * G;
+    const PoolDev& pd = sp.pd[k];
+    const int c = T.u_c[u];
+    const int tot = ldcg_i32(pd.chosen + (size_t)par * pd.cap + c);
+    const int dd = ldcg_i32(pd.dst + (size_t)par * pd.cap + c);
+    const bool inplace = tot == ldcg_i32(pd.refcnt + c);
+    const int d = inplace ? c : dd;
+    T.rm_s[(size_t)u * N + T.u_lab[u]] = d;
+    __stcg(pd.rowmap + ((size_t)(sm.ev & 1) * sp.Ps + slot) * N + T.u_lab[u], d);
+    if (T.u_lead[u]) {
+      if (!inplace) {  // the unit's reserved row is in use now: list it, reserve another
+        pd.live[atomicAdd(pd.ctr, 1)] = d;
+        __stcg(sp.ds[k].n + d, ldcg_i32(sp.ds[k].n + c) + 1);
+        const int fi = atomicSub(pd.ctr + 1, 1) - 1;
+        if (fi < 0) { atomicExch(sp.err, 80); sm.fail = 1; }
+        else T.u_spare[u] = ldcg_i32(pd.freelist + fi);
+      }
+      T.u_duty[u] = inplace ? 1 : 2;
+      T.u_dc[u] = c; T.u_dd[u] = d; T.u_dtot[u] = tot;
+    }
+  }
+}
+
+// this CTA's (max, sum w, sum w^2) over its particles' log-weights; one warp
+__device__ __forceinline__ void pool_cta_partial(const SweepParams& sp, const PoolTables& T, int ns, int par) {
+  const int lane = threadIdx.x & 31;
+  double m = -INFINITY;
+#pragma unroll 1
+  for (int sl = lane; sl < ns; sl += 32) m = fmax(m, T.lw_s[sl]);
+  m = warp_max(m);
+  double s1 = 0.0, s2 = 0.0;
+#pragma unroll 1
+  for (int sl = lane; sl < ns; sl += 32) {
+    const double e = pm_exp(T.lw_s[sl] - m);
+    s1 += e;
+    s2 += e * e;
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    double* ep = sp.ess_part + ((size_t)par * sp.G + blockIdx.x) * 3;
+    __stcg(ep, m); __stcg(ep + 1, s1); __stcg(ep + 2, s2);
+  }
+}
+
+// Combine `cnt` partials (max, s1, s2, stride `str` doubles) in a fixed order; one warp; every lane
+// returns the same bits.
+__device__ __forceinline__ void pool_combine(const double* ep, int cnt, int str, double& mx, double& num, double& den) {
+  const int lane = threadIdx.x & 31;
+  mx = -INFINITY;
+#pragma unroll 1
+  for (int c = lane; c < cnt; c += 32) mx = fmax(mx, ldcg_f64(ep + (size_t)str * c));
+  mx = warp_max(mx);
+  num = 0.0; den = 0.0;
+#pragma unroll 1
+  for (int c = lane; c < cnt; c += 32) {
+    const double e = pm_exp(ldcg_f64(ep + (size_t)str * c) - mx);
+    num += ldcg_f64(ep + (size_t)str * c + 1) * e;
+    den += ldcg_f64(ep + (size_t)str * c + 2) * (e * e);
+  }
+  num = warp_sum(num);
+  den = warp_sum(den);
+}
+
+// Proposal of one unit (dataset k of a particle slot) at step `step`, one warp: src/pmdi.jl:223-265.
+__device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int u, int step,
+                                          int ns) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int K = sp.K, N = sp.N, P = sp.P, par = step & 1;
+  const int Npad = (N + 31) & ~31;
+  const int k = u % K, sl = u / K, slot = (int)blockIdx.x + sl * sp.G;
+  const DsDev& ds = sp.ds[k];
+  const PoolDev& pd = sp.pd[k];
+  const int p = sp.slot0 + slot;  // logical particle
+  double* lps = T.lp_s + (size_t)warp * Npad;
+  const int* rm = T.rm_s + (size_t)u * N;
+  const int J = ds.J, qb = sm.qb[par][k];
+  double uu = 0.0;
+  if (p != 0) uu = sp.tape_alloc ? __ldg(sp.tape_alloc + ((size_t)step * K + k) * P + p)
+                                 : pm_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
+  double mx = -INFINITY;
+  int occ = 0;
+#pragma unroll 1
+  for (int m0 = 0; m0 < N; m0 += 32) {
+    const int m = m0 + lane;
+    double a = -INFINITY;
+    bool o = false;
+    if (m < N) {
+      const int r = rm[m];
+      o = r != pd.cap - 1;
+      const double* pr = ds.part + (long long)r * J;
+      a = ldcg_f64(pr);  // rc[n] + the first block range (E phase), then the others in order
+#pragma unroll 1
+      for (int j = qb; j < J; j += qb) a += ldcg_f64(pr + j);
+      lps[m] = a;
+      if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = a;
+    }
+    occ += __popc(__ballot_sync(FULL, o));
+    mx = fmax(mx, a);
+  }
+  mx = warp_max(mx);
+  __syncwarp();
+  // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
+#pragma unroll 1
+  for (int m = lane; m < N; m += 32) lps[m] = pm_exp(lps[m] - mx) * T.Pi_s[k * N + m];
+  __syncwarp();
+  if (lane == 0) {
+    double run = 0.0;
+#pragma unroll 1
+    for (int m = 0; m < N; ++m) { run += lps[m]; lps[m] = run; }
+  }
+  __syncwarp();
+  const double tot = lps[N - 1];
+  int label;
+  if (p == 0) {
+    label = (int)sp.s_in[(size_t)k * sp.n_obs + sp.order[sp.n1 - 1 + step]] - 1;  // reference trajectory (:262)
+  } else {
+    label = N - 1;
+#pragma unroll 1
+    for (int m0 = 0; m0 < N - 1; m0 += 32) {
+      const int m = m0 + lane;
+      const bool hit = (m < N - 1) && (pm_div(lps[m < N ? m : 0], tot) > uu);  // strict '>' (:255)
+      const unsigned b = __ballot_sync(FULL, hit);
+      if (b) { label = m0 + __ffs(b) - 1; break; }
+    }
+  }
+  int rank = 1;
+  const int c = rm[label];
+  if (lane == 0) rank = atomicAdd(pd.chosen + (size_t)par * pd.cap + c, 1);  // in flight during the log below
+  const double inc = pm_log(tot) + mx;
+  int last_particle = 0;
+  if (lane == 0) {
+    if (rank == 0) __stcg(pd.dst + (size_t)par * pd.cap + c, T.u_spare[u]);  // first chooser: the row a split would use
+    T.u_c[u] = c; T.u_lab[u] = label; T.u_lead[u] = rank == 0;
+    sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
+    if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
+    atomicAdd(&sm.rows_ref[k], (unsigned)occ);
+    // ---- weight increment; the K-th proposal of the particle folds its log-weight
+    T.inc_s[sl * K + k] = inc;
+    T.lab_s[sl * K + k] = label;
+    __threadfence_block();
+    if (atomicAdd(&T.pcount[sl], 1) == K - 1) {
+      __threadfence_block();
+      T.pcount[sl] = 0;
+      const volatile double* iv = T.inc_s + (size_t)sl * K;
+      const volatile int* lv = T.lab_s + (size_t)sl * K;
+      double w = T.lw_s[sl];
+#pragma unroll 1
+      for (int kk = 0; kk < K; ++kk) w += iv[kk];  // dataset order, as src/pmdi.jl:210,233
+      int idx = 0;
+#pragma unroll 1
+      for (int k1 = 0; k1 < K - 1; ++k1)
+#pragma unroll 1
+        for (int k2 = k1 + 1; k2 < K; ++k2) {  // Phi_upweight! (src/misc.jl:50-59)
+          w += (lv[k1] == lv[k2]) ? sp.l1phi[idx] : 0.0;
+          ++idx;
+        }
+      T.lw_s[sl] = w;
+      __stcg(sp.lw + p, w);
+      if (sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
+      __threadfence_block();
+      last_particle = (atomicAdd(&sm.pdone, 1) == ns - 1) ? 1 : 0;
+    }
+  }
+  last_particle = __shfl_sync(FULL, last_particle, 0);
+  if (last_particle) {
+    if (lane == 0) sm.pdone = 0;
+    __threadfence_block();
+    pool_cta_partial(sp, T, ns, par);
+  }
+}
+
+// draw_partstar (src/misc.jl:27-47) by CTA 0, all threads: anc_log[ev][P] (1-based, non-decreasing,
+// anc[0] == 1).  The Fisher-Yates shuffle followed by partstar[1]=1 and sort! only decides WHICH
+// element of the sorted systematic sample the reference particle replaces: the one the shuffle
+// moves to position 1; that index is traced through the swaps without moving anything.
+__device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step, int ev, double mx, int* s_tmp) {
+  const int P = sp.P, t = threadIdx.x;
+  for (int p = t; p < P; p += PMDI_NT) {
+    sp.sc_w[p] = pm_exp(__ldcg(sp.lw + p) - mx);
+    const double us = sp.tape_shuffle ? sp.tape_shuffle[(size_t)step * P + p]
+                                      : pm_uniform(sp.seed, sp.iter, DRAW_SHUFFLE, step, 0, p);
+    int jj = 1 + (int)floor(us * (double)(p + 1));
+    if (jj > p + 1) jj = p + 1;
+    sp.sc_j[p] = jj;
+  }
+  __syncthreads();
+  if (t == 0) {  // pprob = cumsum(exp.(logweight .- max)), sequential (misc.jl:29)
+    double acc = 0.0;
+    for (int p = 0; p < P; ++p) { acc += sp.sc_w[p]; sp.sc_pp[p] = acc; }
+  } else if (t == 32) {  // u, u + 1/P, ... by repeated addition (misc.jl:28,35)
+    const double r = sp.tape_resamp ? sp.tape_resamp[step] : pm_uniform(sp.seed, sp.iter, DRAW_RESAMP, step, 0, 0);
+    double u = r / (double)P;
+    for (int i = 0; i < P; ++i) { sp.sc_u[i] = u; u += 1.0 / (double)P; }
+  } else if (t == 64) {  // index of the pre-shuffle element that ends at position 1
+    int tt = 0;
+    for (int pos = 2; pos <= P; ++pos)
+      if (sp.sc_j[pos - 1] - 1 == tt) tt = pos - 1;
+    s_tmp[0] = tt;
+  }
+  __syncthreads();
+  const double tot = sp.sc_pp[P - 1];
+  for (int i = t; i < P; i += PMDI_NT) {  // first p with pprob[p]/last >= u_i (misc.jl:33-38)
+    const double ui = sp.sc_u[i];
+    int lo = 0, hi = P;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (pm_div(sp.sc_pp[mid], tot) >= ui) hi = mid; else lo = mid + 1;
+    }
+    sp.sc_anc0[i] = (lo < P) ? lo + 1 : P;
+  }
+  __syncthreads();
+  const int drop = s_tmp[0];
+  int* anc = sp.anc_log + (size_t)ev * P;
+  for (int i = t; i < P; i += PMDI_NT) {
+    const int a = (i == 0) ? 1 : ((i - 1 < drop) ? sp.sc_anc0[i - 1] : sp.sc_anc0[i]);
+    anc[i] = a;
+    if (sp.dbg_anc) sp.dbg_anc[(size_t)step * P + i] = a;
+  }
+  __syncthreads();
+  if (t == 0) {
+    int dup = 0;
+    for (int i = 1; i < P; ++i) dup += anc[i] == anc[i - 1];
+    sp.ev_of_step[step] = ev;
+    sp.counters[0] += 1;
+    sp.counters[1] += dup;
+  }
+}
+
+// (re)load the owned units' row maps into shared memory and reserve one row per unit.  All threads.
+__device__ __noinline__ void pool_load_units(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int ns) {
+  const int K = sp.K, N = sp.N, nu = ns * K;
+  for (int i = threadIdx.x; i < nu * N; i += PMDI_NT) {
+    const int u = i / N, m = i - u * N;
+    const int k = u % K, slot = (int)blockIdx.x + (u / K) * sp.G;
+    T.rm_s[i] = ldcg_i32(sp.pd[k].rowmap + ((size_t)(sm.ev & 1) * sp.Ps + slot) * N + m);
+  }
+  for (int u = threadIdx.x; u < nu; u += PMDI_NT) {
+    const PoolDev& pd = sp.pd[u % K];
+    const int fi = atomicSub(pd.ctr + 1, 1) - 1;
+    if (fi < 0) { atomicExch(sp.err, 80); sm.fail = 1; }
+    else T.u_spare[u] = ldcg_i32(pd.freelist + fi);
+  }
+}
+
+// Resampling after step `st` (src/pmdi.jl:318-341): every particle takes its ancestor's row map;
+// references are recounted, rows nobody refers to any more go back to the free list.
+__device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int ns, int st,
+                                           int* s_tmp) {
+  const int K = sp.K, N = sp.N, Ps = sp.Ps;
+  const int ev = sm.ev;
+  const long long gt = (long long)blockIdx.x * PMDI_NT + threadIdx.x, GT = (long long)sp.G * PMDI_NT;
+  if (!pool_gsync(sp, sm)) return false;  // every CTA's deferred bookkeeping is in
+  if (blockIdx.x == 0) pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp);
+  if (!pool_gsync(sp, sm)) return false;
+  const int* anc = sp.anc_log + (size_t)ev * sp.P;
+  if (gt == 0 && st + 1 < sp.steps) {  // rows the E phase evaluated ahead of this decision (live now, dead after it)
+    long long u = 0;
+    for (int k = 0; k < K; ++k) u += ldcg_i32(sp.pd[k].ctr);
+    sp.counters[4] += u;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const PoolDev& pd = sp.pd[k];
+    const int* rm_old = pd.rowmap + (size_t)(ev & 1) * Ps * N;
+    int* rm_new = pd.rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+    for (long long i = gt; i < (long long)Ps * N; i += GT) {
+      const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
+      const int src = ldcg_i32(anc + sp.slot0 + slot) - 1 - sp.slot0;
+      __stcg(rm_new + i, ldcg_i32(rm_old + (size_t)src * N + m));
+    }
+    for (long long r = gt; r < pd.cap; r += GT) __stcg(pd.refcnt + r, 0);
+    if (gt == 0) { __stcg(pd.ctr, 1); __stcg(pd.ctr + 1, 0); }
+  }
+  for (int sl = threadIdx.x; sl < ns; sl += PMDI_NT) T.lw_s[sl] = 1.0;  // logweight .= 1.0 (src/pmdi.jl:319)
+  if (!pool_gsync(sp, sm)) return false;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const PoolDev& pd = sp.pd[k];
+    const int* rm_new = pd.rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+    for (long long i = gt; i < (long long)Ps * N; i += GT) atomicAdd(pd.refcnt + ldcg_i32(rm_new + i), 1);
+  }
+  if (!pool_gsync(sp, sm)) return false;
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const PoolDev& pd = sp.pd[k];
+    for (long long r = gt; r < pd.cap - 1; r += GT) {
+      if (ldcg_i32(pd.refcnt + r) > 0) pd.live[atomicAdd(pd.ctr, 1)] = (int)r;
+      else pd.freelist[atomicAdd(pd.ctr + 1, 1)] = (int)r;
+    }
+    if (gt == 0) { __stcg(pd.refcnt + pd.cap - 1, POOL_BIG_REF); pd.live[0] = pd.cap - 1; }
+  }
+  if (!pool_gsync(sp, sm)) return false;
+  if (gt == 0 && st + 1 < sp.steps) {
+    long long u = 0;
+    for (int k = 0; k < K; ++k) u += ldcg_i32(sp.pd[k].ctr);
+    sp.counters[4] -= u;
+  }
+  if (threadIdx.x == 0) { sm.ev = ev + 1; sm.res_flag = 0; }
+  __syncthreads();
+  pool_load_units(sp, sm, T, ns);  // the new row maps; the units' reserved rows were freed with the dead rows
+  __syncthreads();
+  return !sm.fail;
+}
+
+extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __grid_constant__ SweepParams sp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(16) PoolSmem sm;
+  __shared__ int s_tmp[4];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NW = PMDI_NT / 32;
+  const int cta = blockIdx.x;
+  const int K = sp.K, N = sp.N, steps = sp.steps, G = sp.G;
+  const int Npad = (N + 31) & ~31;
+  const int ns = (sp.Ps - cta + G - 1) / G;  // particle slots cta, cta + G, ...
+  const int nu = ns * K;
+  const int MS = (sp.Ps + G - 1) / G, MU = MS * K;
+
+  // dynamic shared memory: [observation ring][lf table][lp scratch][Pi][lw][inc][unit tables]
+  unsigned char* xring = smem_raw;
+  PoolTables T;
+  T.lf = (double*)(smem_raw + (size_t)sp.obs_ring * sp.sm_x_bytes);
+  T.lp_s = T.lf + sp.lf_T;
+  T.Pi_s = T.lp_s + (size_t)NW * Npad;
+  T.lw_s = T.Pi_s + (size_t)K * N;
+  T.inc_s = T.lw_s + MS;
+  T.lab_s = (int*)(T.inc_s + MU);
+  T.pcount = T.lab_s + MU;
+  T.u_c = T.pcount + MS;
+  T.u_lab = T.u_c + MU;
+  T.u_lead = T.u_lab + MU;
+  T.u_duty = T.u_lead + MU;
+  T.u_dc = T.u_duty + MU;
+  T.u_dd = T.u_dc + MU;
+  T.u_dtot = T.u_dd + MU;
+  T.u_spare = T.u_dtot + MU;
+  T.rm_s = T.u_spare + MU;
+  for (int i = tid; i < sp.lf_T; i += PMDI_NT) T.lf[i] = sp.lf_glob[i];
+  for (int i = tid; i < K * N; i += PMDI_NT) T.Pi_s[i] = sp.Pi[i];
+  for (int sl = tid; sl < ns; sl += PMDI_NT) { T.lw_s[sl] = sp.lw_init; T.pcount[sl] = 0; }
+  for (int u = tid; u < nu; u += PMDI_NT) T.u_duty[u] = 0;
+  if (tid < PMDI_MAX_K) { sm.rows_eval[tid] = 0; sm.rows_ref[tid] = 0; }
+  if (tid < 8) sm.tacc[tid] = 0;
+  if (tid == 0) {
+    sm.res_flag = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.epoch = 0; sm.res_mx = 0.0;
+    for (int b = 0; b < sp.obs_ring; ++b) mbar_init(&sm.obs_bar[b], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    pool_snapshot(sp, sm, 0);
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int s = 0; s < sp.obs_ring; ++s) pool_issue_obs(sp, s, xring, sm.obs_bar);
+  pool_load_units(sp, sm, T, ns);
+
+  const bool timing = sp.phase_ns != nullptr;
+  unsigned long long tw_prev = timing ? globaltimer_ns() : 0ull;
+#define PHASE_MARK(i_)                                                 \
+  if (timing && lane == 0) {                                           \
+    const unsigned long long now_ = globaltimer_ns();                  \
+    atomicAdd(&sm.tacc[i_], now_ - tw_prev);                           \
+    tw_prev = now_;                                                    \
+  }
+
+  int obs_ok = -1;
+  pool_eval_phase(sp, sm, T, 0, -1, xring, obs_ok);
+  PHASE_MARK(1)
+  if (!pool_gsync(sp, sm)) return;  // B1(0)
+  PHASE_MARK(0)
+#pragma unroll 1
+  for (int t = 0; t < steps; ++t) {
+    const int par = t & 1;
+    // ---- P(t)
+    if (t > 0) {
+      if (tid == 0) pool_issue_obs(sp, t - 1 + sp.obs_ring, xring, sm.obs_bar);  // x[t-1] is dead: its slot refills
+      pool_duties(sp, T, nu, par ^ 1);
+      if (sm.res_flag) {
+        if (!pool_resample(sp, sm, T, ns, t - 1, s_tmp)) return;
+        PHASE_MARK(6)
+      }
+    }
+    if (tid == 0 && t + 1 < steps) pool_snapshot(sp, sm, par ^ 1);  // item list of E(t+1): the rows live now
+#pragma unroll 1
+    for (int u = warp; u < nu; u += NW) pool_propose(sp, sm, T, u, t, ns);
+    PHASE_MARK(2)
+    if (!pool_gsync(sp, sm)) return;  // B2(t): every choice, reservation and ESS partial is in
+    PHASE_MARK(0)
+    // ---- R(t)
+    pool_resolve_units(sp, sm, T, nu, par);
+    if (warp == NW - 1) {  // calc_ESS (src/misc.jl:15-25), same bits in every CTA; the last warp has the fewest items
+      double mxv, num, den;
+      pool_combine(sp.ess_part + (size_t)par * G * 3, G, 3, mxv, num, den);
+      if (lane == 0) {
+        const bool res = (num * num) / den <= 0.5 * (double)sp.P;  // src/pmdi.jl:317
+        sm.res_mx = mxv;
+        sm.res_flag = res ? 1 : 0;
+        if (!res && cta == 0) sp.ev_of_step[t] = -1;
+      }
+    }
+    PHASE_MARK(3)
+    // ---- E(t+1)
+    if (t + 1 < steps) pool_eval_phase(sp, sm, T, t + 1, par, xring, obs_ok);
+    PHASE_MARK(1)
+    if (!pool_gsync(sp, sm)) return;  // B1(t+1)
+    PHASE_MARK(0)
+  }
+  // ---- after the last observation: its bookkeeping (cluster sizes), and its ESS test
+  pool_duties(sp, T, nu, (steps - 1) & 1);
+  __syncthreads();
+  const int final_res = sm.res_flag;
+  if (final_res && !pool_resample(sp, sm, T, ns, steps - 1, s_tmp)) return;
+  if (tid < K) {
+    atomicAdd(sp.rows_eval + tid, (unsigned long long)sm.rows_eval[tid]);
+    atomicAdd(sp.rows_ref + tid, (unsigned long long)sm.rows_ref[tid]);
+  }
+  if (cta == 0)  // after a final resampling all log-weights are 1.0 (src/pmdi.jl:319)
+    for (int p = tid; p < sp.P; p += PMDI_NT) sp.lw_out[p] = final_res ? 1.0 : __ldcg(sp.lw + p);
+  if (timing && tid < 8) sp.phase_ns[(size_t)cta * 8 + tid] = sm.tacc[tid] / NW;
+  if (cta == 0 && tid == 0) sp.counters[2] = sm.ev;
+#undef PHASE_MARK
+}
+
+// ------------------------------------------------------------------------------------------------
+// set-up and finish kernels of the pool engine
+// ------------------------------------------------------------------------------------------------
+
+// all rows of a dataset's packed categorical counts to zero (the other statistics: k_init_rows)
+__global__ void k_pool_init_rows(PoolDev pd, long long words) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) pd.cw[i] = 0ull;
+}
+
+// Start of a sweep: the rho-prefix clusters (rows 0..N-1, built by k_prefix_build / k_proto_aux) are
+// shared by all particles (src/pmdi.jl:197-199: particle[u,:,k] .= id; clusters_counts = particles).
+// One block per dataset.
+__global__ void k_pool_init(SweepParams sp) {
+  const int k = blockIdx.x, t = threadIdx.x, NT = blockDim.x, N = sp.N, Ps = sp.Ps;
+  const PoolDev pd = sp.pd[k];
+  const DsDev& ds = sp.ds[k];
+  __shared__ int s_nfree0;
+  for (int i = t; i < 2 * pd.cap; i += NT) { pd.chosen[i] = 0; pd.dst[i] = -1; }
+  for (int r = t; r < pd.cap; r += NT) pd.refcnt[r] = (r < N && ds.n[r] > 0) ? Ps : 0;
+  for (long long i = t; i < (long long)Ps * N; i += NT) {
+    const int m = (int)(i % N);
+    pd.rowmap[i] = ds.n[m] > 0 ? m : pd.cap - 1;
+  }
+  if (t == 0) {
+    int nl = 0, nf = 0;
+    pd.live[nl++] = pd.cap - 1;
+    for (int m = 0; m < N; ++m) {
+      if (ds.n[m] > 0) pd.live[nl++] = m;
+      else pd.freelist[nf++] = m;
+    }
+    pd.ctr[0] = nl;
+    pd.ctr[1] = nf + (pd.cap - 1 - N);
+    s_nfree0 = nf;
+  }
+  __syncthreads();
+  const int nf0 = s_nfree0;
+  for (int r = N + t; r < pd.cap - 1; r += NT) pd.freelist[nf0 + (r - N)] = r;
+  __syncthreads();
+  if (t == 0) { pd.refcnt[pd.cap - 1] = POOL_BIG_REF; ds.n[pd.cap - 1] = 0; }
+}
+
+// packed categorical counts of the prefix prototypes from the member lists (rows 0..N-1):
+// grid (ceil(Dp/128), N), thread per feature
+__global__ void k_pool_prefix_cat(SweepParams sp, int k, const int* members, const int* off) {
+  const int m = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
+  const DsDev& ds = sp.ds[k];
+  const PoolDev& pd = sp.pd[k];
+  if (q >= ds.Dp) return;
+  const int b = off[k * (sp.N + 1) + m], e = off[k * (sp.N + 1) + m + 1];
+  const int* mem = members + (size_t)k * (sp.n1 - 1) + b;
+  unsigned long long* w = pd.cw + ((size_t)m * ds.Dp + q) * pd.wpf;
+  for (int i = 0; i < pd.wpf; ++i) w[i] = 0ull;
+  if (ds.flag[q]) {
+    const int* x = (const int*)ds.x;
+    const int fw = 64 / pd.fpw;
+    for (int t = 0; t < e - b; ++t) {
+      const int lv = x[(size_t)mem[t] * ds.Dp + q] - 1;
+      w[lv / pd.fpw] += 1ull << ((lv % pd.fpw) * fw);
+    }
+  }
+}
+
+// Particle selection (src/pmdi.jl:345-350), lineage back-trace, s[:] = sstar[p_star,:,:] (:373),
+// plus the reductions the host's update_hypers reads (src/update_hypers.jl:72,109-115): label counts
+// per (label, dataset) and, per dataset pair, the number of observations with equal labels.
+__global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long long* p_star_out,
+                              long long* cluster_n, int* cur_at, long long* label_counts, long long* pair_agree) {
+  const int t = threadIdx.x, NT = blockDim.x, P = sp.P, K = sp.K, N = sp.N;
+  __shared__ double red[32];
+  double mx = -INFINITY;
+  for (int p = t; p < P; p += NT) mx = fmax(mx, sp.lw_out[p]);
+  mx = warp_max(mx);
+  if ((t & 31) == 0) red[t >> 5] = mx;
+  __syncthreads();
+  mx = red[0];
+  for (int i = 1; i < (NT >> 5); ++i) mx = fmax(mx, red[i]);
+  for (int p = t; p < P; p += NT) sp.sc_w[p] = exp(sp.lw_out[p] - mx);
+  __syncthreads();
+  if (t == 0) {
+    double tot = 0.0;
+    for (int p = 0; p < P; ++p) tot += sp.sc_w[p];
+    const double u = sp.tape_select ? sp.tape_select[0] : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_SELECT, 0, 0, 0);
+    const double thr = u * tot;
+    int i = 0;
+    double cw = sp.sc_w[0];
+    while (cw < thr && i < P - 1) { ++i; cw += sp.sc_w[i]; }
+    *p_star_out = i + 1;
+    int cur = i;  // lineage of p_star through the resampling events, backwards (src/__pmdi.jl:285)
+    for (int st = sp.steps - 1; st >= 0; --st) {
+      const int ev = sp.ev_of_step[st];
+      if (ev >= 0 && !compat) cur = sp.anc_log[(size_t)ev * P + cur] - 1;
+      cur_at[st] = cur;
+    }
+  }
+  for (size_t i = t; i < (size_t)K * sp.n_obs; i += NT) s_out[i] = sp.s_in[i];
+  for (int i = t; i < N * K; i += NT) label_counts[i] = 0;
+  for (int i = t; i < K * (K - 1) / 2; i += NT) pair_agree[i] = 0;
+  __syncthreads();
+  for (int idx = t; idx < sp.steps * K; idx += NT) {
+    const int st = idx / K, k = idx - st * K;
+    const int obs = sp.order[sp.n1 - 1 + st];
+    s_out[(size_t)k * sp.n_obs + obs] = 1 + sp.alloc_log[((size_t)st * K + k) * P + cur_at[st]];
+  }
+  __syncthreads();
+  for (size_t i = t; i < (size_t)K * sp.n_obs; i += NT)
+    atomicAdd((unsigned long long*)&label_counts[(i / sp.n_obs) * N + (s_out[i] - 1)], 1ull);
+  for (int i = t; i < sp.n_obs; i += NT) {
+    int idx = 0;
+    for (int k1 = 0; k1 < K - 1; ++k1)
+      for (int k2 = k1 + 1; k2 < K; ++k2) {
+        if (s_out[(size_t)k1 * sp.n_obs + i] == s_out[(size_t)k2 * sp.n_obs + i])
+          atomicAdd((unsigned long long*)&pair_agree[idx], 1ull);
+        ++idx;
+      }
+  }
+  if (cluster_n && sp.engine == 0) {
+    const int ev = (int)sp.counters[2];
+    const int* slot = sp.slot_of + (ev & 1) * P;
+    for (size_t idx = t; idx < (size_t)K * P * N; idx += NT) {
+      const int k = (int)(idx / ((size_t)P * N));
+      const size_t rem = idx - (size_t)k * P * N;
+      const int p = (int)(rem / N), m = (int)(rem % N);
+      const int ls = slot[p] - sp.slot0;  // clusters of particles held by another rank: -1
+      cluster_n[idx] = (ls >= 0 && ls < sp.Ps) ? sp.ds[k].n[(long long)ls * N + m] : -1;
+    }
+  }
+  if (cluster_n && sp.engine == 1) {
+    const int ev = (int)sp.counters[2];
+    for (size_t idx = t; idx < (size_t)K * P * N; idx += NT) {
+      const int k = (int)(idx / ((size_t)P * N));
+      const size_t rem = idx - (size_t)k * P * N;
+      const int p = (int)(rem / N), m = (int)(rem % N);
+      const int ls = p - sp.slot0;  // clusters of particles held by another rank: -1
+      long long v = -1;
+      if (ls >= 0 && ls < sp.Ps) {
+        const PoolDev& pd = sp.pd[k];
+        v = sp.ds[k].n[pd.rowmap[((size_t)(ev & 1) * sp.Ps + ls) * N + m]];
+      }
+      cluster_n[idx] = v;
+    }
+  }
+}

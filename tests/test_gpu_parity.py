@@ -14,9 +14,14 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-5  # north_star tolerance for floating-point outputs
 
 
-def _run_both(pr, tapes=None, seed=11, it=3, lw0=0.0, flags=None):
+ENGINES = ["pool", "dense"]  # copy-on-write pool (default) and the dense form, selected by PMDI_ENGINE
+
+
+def _run_both(pr, tapes=None, seed=11, it=3, lw0=0.0, flags=None, engine="pool"):
+    import os
     from oracle import oracle as orc
     import pmdi_b200.capi as capi
+    os.environ["PMDI_ENGINE"] = engine
     o = orc.Oracle(pr["data"], pr["types"], pr["N"], pr["P"])
     ctx = capi.Context(pr["data"], pr["types"], pr["N"], pr["P"])
     if flags is not None:
@@ -28,6 +33,8 @@ def _run_both(pr, tapes=None, seed=11, it=3, lw0=0.0, flags=None):
     got = ctx.sweep(pr["s"], pr["order"], pr["n1"], pr["Pi"], pr["phi"], logweight_init=lw0,
                     seed=seed, it=it, tapes=tapes, debug=True)
     ctx.close()
+    os.environ.pop("PMDI_ENGINE", None)
+    assert got["engine"] == engine
     return ref, got
 
 
@@ -57,40 +64,63 @@ CASES = {
 }
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", list(CASES))
-def test_sweep_matches_oracle_philox(name):
+def test_sweep_matches_oracle_philox(name, engine):
     pr = problem(**CASES[name], seed=3)
-    ref, got = _run_both(pr)
+    ref, got = _run_both(pr, engine=engine)
     _assert_parity(pr, ref, got)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", ["gauss_small", "mixed_k3"])
-def test_sweep_matches_oracle_tapes(name):
+def test_sweep_matches_oracle_tapes(name, engine):
     """Deterministic mode proper: the uniforms are fed in as tapes."""
     pr = problem(**CASES[name], seed=4)
-    ref, got = _run_both(pr, tapes=tapes_for(pr), lw0=1.0)
+    ref, got = _run_both(pr, tapes=tapes_for(pr), lw0=1.0, engine=engine)
     _assert_parity(pr, ref, got)
     if name == "mixed_k3":
         assert ref["n_resamples"] > 0  # the resampling path is exercised
 
 
-def test_sweep_with_feature_flags():
+@pytest.mark.parametrize("engine", ENGINES)
+def test_sweep_with_feature_flags(engine):
     pr = problem(**CASES["mixed_k3"], seed=6)
     rng = np.random.default_rng(0)
     flags = [(rng.random(d.shape[1]) < 0.6).astype(np.uint8) for d in pr["data"]]
-    ref, got = _run_both(pr, flags=flags)
+    ref, got = _run_both(pr, flags=flags, engine=engine)
     _assert_parity(pr, ref, got)
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", ["gauss_wide", "mixed_k3", "mixed_k2_manyP"])
 @pytest.mark.parametrize("qb", ["1", "8"])
-def test_parity_for_other_item_sizes(name, qb, monkeypatch):
-    """The number of 256-feature blocks per plain work item is chosen per workload (whole rows when a
-    CTA owns many units); parity must not depend on it."""
+def test_parity_for_other_item_sizes(name, qb, engine, monkeypatch):
+    """The number of 256-feature blocks per work item is chosen per workload / per step (whole rows when
+    there are many rows per warp); parity must not depend on it."""
     monkeypatch.setenv("PMDI_QB", qb)
     pr = problem(**CASES[name], seed=5)
-    ref, got = _run_both(pr, lw0=1.0)
+    ref, got = _run_both(pr, lw0=1.0, engine=engine)
     _assert_parity(pr, ref, got)
+
+
+@pytest.mark.parametrize("name", ["gauss_iris_shape", "mixed_k3", "mixed_k2_manyP", "gauss_N40"])
+def test_pool_evaluates_each_distinct_cluster_once(name):
+    """The copy-on-write pool performs exactly the reference's calc_logprob calls: one per distinct
+    cluster per (observation, dataset) - the oracle's de-duplicated mode counts them the way
+    src/__pmdi.jl:187 does (n_operations)."""
+    from oracle import oracle as orc
+    pr = problem(**CASES[name], seed=7)
+    ref, got = _run_both(pr, lw0=1.0, engine="pool")
+    _assert_parity(pr, ref, got)
+    o = orc.Oracle(pr["data"], pr["types"], pr["N"], pr["P"])
+    dd = o.sweep(pr["s"], pr["order"], pr["n1"], pr["Pi"], pr["phi"], mode=orc.MODE_DEDUP, logweight_init=1.0,
+                 seed=11, it=3)
+    np.testing.assert_array_equal(dd["s"], got["s"])
+    # evaluation runs one observation ahead of the resampling decision: rows that a resampling removes were
+    # evaluated once more than in the reference; the kernel counts them
+    assert sum(got["rows_evaluated"]) - got["rows_evaluated_ahead"] == dd["n_ops"]
+    assert sum(got["rows_referenced"]) >= sum(got["rows_evaluated"]) - pr["K"] * (pr["n"] - pr["n1"] + 1)
 
 
 def test_sstar_compat_flag():
@@ -116,10 +146,11 @@ EDGE = {
 }
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("name", list(EDGE))
-def test_edge_cases(name):
+def test_edge_cases(name, engine):
     pr = problem(**EDGE[name], seed=10)
-    ref, got = _run_both(pr, lw0=1.0)
+    ref, got = _run_both(pr, lw0=1.0, engine=engine)
     _assert_parity(pr, ref, got)
 
 
