@@ -131,6 +131,7 @@ struct pmdi_ctx {
   DevBuf<unsigned long long> rows_eval, rows_ref, phase_ns, trace;
   DevBuf<long long> label_counts, pair_agree;
   DevBuf<double> rank_part;
+  DevBuf<int4> pull_jobs;
   DevBuf<double> dbg_lp, dbg_lw, scratch_d;
   DevBuf<int> dbg_alloc, dbg_anc, scratch_i, wd_state;
   DevBuf<uint8_t> scratch_u8;
@@ -240,14 +241,15 @@ int build_layout(pmdi_ctx* c) {
   if (c->R > 1 && c->peer_base[c->rank] != nullptr)
     return fail(1, "pmdi: datasets cannot be re-bound after pmdi_ipc_export (the peers hold this layout)");
   // engine: the copy-on-write pool unless PMDI_ENGINE=dense asks for the dense form (every particle owns its
-  // N rows); particle sharding over several GPUs runs on the dense engine
+  // N rows)
   const char* eng = getenv("PMDI_ENGINE");
   c->engine = (eng && std::string(eng) == "dense") ? 0 : 1;
-  if (c->R > 1 && !(eng && std::string(eng) == "pool")) c->engine = 0;
   if (getenv("PMDI_WATCHDOG_S")) c->wd_ns = (unsigned long long)(atof(getenv("PMDI_WATCHDOG_S")) * 1e9);
   // dense: particle slots, prototypes, the shared empty row.  pool: at most Ps*N live rows, one reservation per
-  // chosen row in flight (<= Ps per dataset), the N prefix rows, the empty cluster
-  const long long rows = c->engine ? (long long)c->Ps * c->N + c->Ps + c->N + 2 : (long long)(c->Ps + 2) * c->N;
+  // chosen row in flight (<= Ps per dataset), the N prefix rows, the empty cluster; with several ranks a
+  // resampling pulls the rows of remote ancestors before the dead local rows are freed (another Ps*N at most)
+  const long long rows = c->engine ? (long long)(c->R > 1 ? 2 : 1) * c->Ps * c->N + c->Ps + c->N + 2
+                                   : (long long)(c->Ps + 2) * c->N;
   if (rows > 0x7fffff00ll) return fail(1, "pmdi: particles x N too large");
   const int Gmax = std::min(c->n_sm, c->Ps);
   size_t off_b = 0;
@@ -496,6 +498,8 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   for (auto* b : dl) b->release();
   c->lab.release(); c->alloc_log.release(); c->copies.release(); c->bar.release();
   c->rows_eval.release(); c->phase_ns.release(); c->scratch_u8.release();
+  c->rows_ref.release(); c->trace.release(); c->wd_state.release(); c->pull_jobs.release(); c->rank_part.release();
+  c->label_counts.release(); c->pair_agree.release();
   for (int r = 0; r < c->R; ++r)
     if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
   if (c->arena) cudaFree(c->arena);
@@ -723,6 +727,11 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   CK(c->cur_at.ensure(steps));
   CK(c->rows_ref.ensure(PMDI_MAX_K)); CK(c->label_counts.ensure((size_t)N * K)); CK(c->pair_agree.ensure(std::max(npairs, 1)));
   sp.rows_ref = c->rows_ref.p;
+  sp.pull_jobs = nullptr;
+  if (c->engine && c->R > 1) {
+    CK(c->pull_jobs.ensure((size_t)K * c->Ps * N));
+    sp.pull_jobs = c->pull_jobs.p;
+  }
   sp.n1 = (int)a->n1; sp.steps = steps; sp.flags = (int)a->flags;
   sp.Pi = c->Pi.p; sp.l1phi = c->l1phi.p; sp.s_in = c->s_in.p; sp.order = c->order.p;
   sp.lw_init = a->logweight_init; sp.seed = a->seed; sp.iter = a->iter;
@@ -748,6 +757,7 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   if (c->R > 1 && c->peer_base[c->rank] == nullptr)
     return fail(1, "pmdi_sweep: call pmdi_ipc_export / pmdi_ipc_import on every rank first");
   CK(cudaMemsetAsync(c->bar.p, 0, 16, st));  // with R > 1 the caller barriers all ranks between upload and run
+  CK(cudaMemsetAsync(c->rank_part.p, 0, sizeof(double) * 2 * 8 * 4, st));  // the step tags of the previous sweep
   CK(cudaMemsetAsync(c->phase_ns.p, 0, 64 * (size_t)c->G, st));
   CK(c->wd_state.ensure((size_t)c->G * 16 * 16));
   CK(cudaMemsetAsync(c->wd_state.p, 0xff, sizeof(int) * (size_t)c->G * 16 * 16, st));

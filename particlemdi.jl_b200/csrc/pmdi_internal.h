@@ -77,6 +77,7 @@ struct SweepParams {
   int obs_ring;           /* depth of the shared-memory observation ring (2..4)              */
   long long proto_base;   /* first row of the rho-prefix prototypes (dense: Ps*N, pool: 0)   */
   unsigned long long wd_ns; /* watchdog of the in-kernel waits                               */
+  int4* pull_jobs;        /* resampling: (dataset, source rank, source row, local row) of rows to pull */
   double* rank_part;      /* [2][R][4] per step parity and rank: max, sum w, sum w^2, step tag */
   unsigned long long* rows_ref; /* [K] occupied (particle, label) rows referenced by proposals */
   const double* Pi;      /* [K][N]                                          */

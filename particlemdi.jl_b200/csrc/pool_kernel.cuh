@@ -35,6 +35,7 @@
 struct PoolSmem {
   unsigned long long obs_bar[PMDI_OBS_RING];
   unsigned long long epoch;    // local grid-barrier arrivals expected so far
+  unsigned long long xepoch;   // cross-rank barrier arrivals expected so far (one per rank)
   double res_mx;
   int res_flag;                // the last resolved step resamples
   int fail;
@@ -67,11 +68,12 @@ struct PoolTables {
 };
 
 // local grid barrier (this GPU's CTAs), all threads
-__device__ __noinline__ bool pool_gsync(const SweepParams& sp, PoolSmem& sm) {
+// (sys: this CTA's peer stores are made visible system-wide before it arrives - the cross-rank barrier)
+__device__ __noinline__ bool pool_gsync(const SweepParams& sp, PoolSmem& sm, bool sys = false) {
   __syncthreads();
   if (threadIdx.x == 0) {
     sm.epoch += (unsigned long long)sp.G;
-    __threadfence();
+    if (sys) __threadfence_system(); else __threadfence();
     atomicAdd((unsigned long long*)sp.bar, 1ull);
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
@@ -86,6 +88,32 @@ __device__ __noinline__ bool pool_gsync(const SweepParams& sp, PoolSmem& sm) {
   }
   __syncthreads();
   return sm.fail == 0;
+}
+
+// barrier over the CTAs of ALL ranks: local barrier, one arrival per rank on every rank's counter
+// (NVLink peer atomics), local barrier.  Resampling only.
+__device__ __noinline__ bool pool_xsync(const SweepParams& sp, PoolSmem& sm) {
+  if (!pool_gsync(sp, sm, sp.R > 1)) return false;
+  if (sp.R > 1) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long* xbar = (unsigned long long*)sp.bar + 1;
+      sm.xepoch += (unsigned long long)sp.R;
+      __threadfence_system();
+#pragma unroll 1
+      for (int r = 0; r < sp.R; ++r) atomicAdd_system(on_rank(sp, xbar, r), 1ull);
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned spins = 0;
+      while (ld_acquire_sys_u64(xbar) < sm.xepoch) {
+        if (((++spins) & 0x3ffu) == 0) {
+          if (__ldcg(sp.err) != 0) break;
+          if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); break; }
+        }
+      }
+      __threadfence_system();
+    }
+    if (!pool_gsync(sp, sm)) return false;
+  }
+  return true;
 }
 
 // one thread: bulk-copy the K rows of the observation swept at `step` into its ring slot
@@ -227,6 +255,7 @@ __device__ __noinline__ void pool_eval_phase(const SweepParams& sp, PoolSmem& sm
       if (lane == 0) {
         if (q == 0) { v = __ldg(ds.rc + nc) + v; atomicAdd(&sm.rows_eval[k], 1u); }  // rc first: the order of the sum
         __stcg(ds.part + (long long)c * ds.J + j0, v);
+        for (int j = j0 + 1; j < j1; ++j) __stcg(ds.part + (long long)c * ds.J + j, 0.0);
       }
     } else if (tot == ldcg_i32(pd.refcnt + c)) {  // every reference chose it: in place (src/pmdi.jl:284-286)
       double dummy;
@@ -234,6 +263,7 @@ __device__ __noinline__ void pool_eval_phase(const SweepParams& sp, PoolSmem& sm
       if (lane == 0) {
         if (q == 0) { v = __ldg(ds.rc + nc + 1) + v; atomicAdd(&sm.rows_eval[k], 1u); }
         __stcg(ds.part + (long long)c * ds.J + j0, v);
+        for (int j = j0 + 1; j < j1; ++j) __stcg(ds.part + (long long)c * ds.J + j, 0.0);
       }
     } else {  // split: the choosers' copy goes to row d, the others keep c (src/pmdi.jl:288-309)
       const int d = ldcg_i32(pd.dst + (size_t)pp * pd.cap + c);
@@ -247,6 +277,10 @@ __device__ __noinline__ void pool_eval_phase(const SweepParams& sp, PoolSmem& sm
         }
         __stcg(ds.part + (long long)c * ds.J + j0, vs);
         __stcg(ds.part + (long long)d * ds.J + j0, vd);
+        for (int j = j0 + 1; j < j1; ++j) {
+          __stcg(ds.part + (long long)c * ds.J + j, 0.0);
+          __stcg(ds.part + (long long)d * ds.J + j, 0.0);
+        }
       }
     }
   }
@@ -353,7 +387,7 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
   const int p = sp.slot0 + slot;  // logical particle
   double* lps = T.lp_s + (size_t)warp * Npad;
   const int* rm = T.rm_s + (size_t)u * N;
-  const int J = ds.J, qb = sm.qb[par][k];
+  const int J = ds.J;
   double uu = 0.0;
   if (p != 0) uu = sp.tape_alloc ? __ldg(sp.tape_alloc + ((size_t)step * K + k) * P + p)
                                  : pm_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
@@ -368,9 +402,9 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
       const int r = rm[m];
       o = r != pd.cap - 1;
       const double* pr = ds.part + (long long)r * J;
-      a = ldcg_f64(pr);  // rc[n] + the first block range (E phase), then the others in order
-#pragma unroll 1
-      for (int j = qb; j < J; j += qb) a += ldcg_f64(pr + j);
+      a = ldcg_f64(pr);  // rc[n] + the first block range (E phase), then the other ranges in order;
+#pragma unroll 1           // slots inside a range hold 0.0 (x + 0.0 == x): the layout needs no item size
+      for (int j = 1; j < J; ++j) a += ldcg_f64(pr + j);
       lps[m] = a;
       if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = a;
     }
@@ -411,7 +445,9 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
   if (lane == 0) {
     if (rank == 0) __stcg(pd.dst + (size_t)par * pd.cap + c, T.u_spare[u]);  // first chooser: the row a split would use
     T.u_c[u] = c; T.u_lab[u] = label; T.u_lead[u] = rank == 0;
-    sp.alloc_log[((size_t)step * K + k) * P + p] = (uint8_t)label;
+#pragma unroll 1
+    for (int r = 0; r < sp.R; ++r)  // every rank back-traces the selected particle's lineage itself
+      *on_rank(sp, sp.alloc_log + ((size_t)step * K + k) * P + p, r) = (uint8_t)label;
     if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
     atomicAdd(&sm.rows_ref[k], (unsigned)occ);
     // ---- weight increment; the K-th proposal of the particle folds its log-weight
@@ -456,7 +492,7 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
 __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step, int ev, double mx, int* s_tmp) {
   const int P = sp.P, t = threadIdx.x;
   for (int p = t; p < P; p += PMDI_NT) {
-    sp.sc_w[p] = pm_exp(__ldcg(sp.lw + p) - mx);
+    sp.sc_w[p] = pm_exp(__ldcg(on_rank(sp, sp.lw + p, p / sp.Ps)) - mx);  // the holder's copy (NVLink when remote)
     const double us = sp.tape_shuffle ? sp.tape_shuffle[(size_t)step * P + p]
                                       : pm_uniform(sp.seed, sp.iter, DRAW_SHUFFLE, step, 0, p);
     int jj = 1 + (int)floor(us * (double)(p + 1));
@@ -522,14 +558,47 @@ __device__ __noinline__ void pool_load_units(const SweepParams& sp, PoolSmem& sm
   }
 }
 
+// One warp copies pool row `src` of the rank whose arena is `sdelta` bytes away into local row `dst`:
+// statistics, aux, the row's current predictive partials, the cluster size.
+__device__ __noinline__ void pool_row_pull(const SweepParams& sp, int k, long long sdelta, long long src, long long dst) {
+  const DsDev& ds = sp.ds[k];
+  const int lane = threadIdx.x & 31, Dp = ds.Dp;
+#define PMDI_SRC(ptr_) ((decltype(ptr_))((const char*)(ptr_) + sdelta))
+  if (ds.type == T_GAUSSIAN) {
+    for (int q = 2 * lane; q < Dp; q += 64) {
+      const double2 a = ldcg_f64x2(PMDI_SRC(ds.mu) + src * Dp + q), b = ldcg_f64x2(PMDI_SRC(ds.lamn) + src * Dp + q);
+      const double2 c = ldcg_f64x2(PMDI_SRC(ds.sum) + src * Dp + q), d = ldcg_f64x2(PMDI_SRC(ds.beta) + src * Dp + q);
+      *(double2*)(ds.mu + dst * Dp + q) = a; *(double2*)(ds.lamn + dst * Dp + q) = b;
+      *(double2*)(ds.sum + dst * Dp + q) = c; *(double2*)(ds.beta + dst * Dp + q) = d;
+    }
+  } else if (ds.type == T_CATEGORICAL) {
+    const PoolDev& pd = sp.pd[k];
+    const long long W = (long long)Dp * pd.wpf;
+    for (long long q = 2 * lane; q < W; q += 64)
+      *(ulonglong2*)(pd.cw + dst * W + q) = ldcg_u64x2(PMDI_SRC(pd.cw) + src * W + q);
+  } else {
+    for (int q = 2 * lane; q < Dp; q += 64)
+      *(longlong2*)(ds.S + dst * Dp + q) = ldcg_i64x2(PMDI_SRC(ds.S) + src * Dp + q);
+  }
+  for (int jj = lane; jj < ds.J; jj += 32) {
+    ds.aux[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + jj);
+    ds.part[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.part) + src * ds.J + jj);
+  }
+  if (lane == 0) ds.n[dst] = ldcg_i32(PMDI_SRC(ds.n) + src);
+#undef PMDI_SRC
+}
+
 // Resampling after step `st` (src/pmdi.jl:318-341): every particle takes its ancestor's row map;
-// references are recounted, rows nobody refers to any more go back to the free list.
+// references are recounted, rows nobody refers to any more go back to the free list.  An ancestor
+// held by another rank has its occupied rows pulled into this rank's pool through NVLink peer
+// memory (once per ancestor: its children here share the copies).
 __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int ns, int st,
                                            int* s_tmp) {
   const int K = sp.K, N = sp.N, Ps = sp.Ps;
   const int ev = sm.ev;
   const long long gt = (long long)blockIdx.x * PMDI_NT + threadIdx.x, GT = (long long)sp.G * PMDI_NT;
-  if (!pool_gsync(sp, sm)) return false;  // every CTA's deferred bookkeeping is in
+  // every CTA of every rank: deferred bookkeeping in, this step's log-weights and evaluations final
+  if (!pool_xsync(sp, sm)) return false;
   if (blockIdx.x == 0) pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp);
   if (!pool_gsync(sp, sm)) return false;
   const int* anc = sp.anc_log + (size_t)ev * sp.P;
@@ -538,7 +607,7 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
     for (int k = 0; k < K; ++k) u += ldcg_i32(sp.pd[k].ctr);
     sp.counters[4] += u;
   }
-  __syncthreads();
+  // ---- A1: row maps of children of local ancestors; first local child of a remote ancestor reserves rows
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
     const PoolDev& pd = sp.pd[k];
@@ -546,13 +615,53 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
     int* rm_new = pd.rowmap + (size_t)((ev + 1) & 1) * Ps * N;
     for (long long i = gt; i < (long long)Ps * N; i += GT) {
       const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
-      const int src = ldcg_i32(anc + sp.slot0 + slot) - 1 - sp.slot0;
-      __stcg(rm_new + i, ldcg_i32(rm_old + (size_t)src * N + m));
+      const int a = ldcg_i32(anc + sp.slot0 + slot) - 1;
+      const int ra = a / Ps, la = a - ra * Ps;
+      if (ra == sp.rank) {
+        __stcg(rm_new + i, ldcg_i32(rm_old + (size_t)la * N + m));
+      } else if (slot == 0 || ldcg_i32(anc + sp.slot0 + slot - 1) != a + 1) {
+        const int rb = ldcg_i32(on_rank(sp, rm_old, ra) + (size_t)la * N + m);
+        int d = pd.cap - 1;
+        if (rb != pd.cap - 1) {
+          const int fi = atomicSub(pd.ctr + 1, 1) - 1;
+          if (fi < 0) { atomicExch(sp.err, 80); }
+          else {
+            d = ldcg_i32(pd.freelist + fi);
+            const long long job = atomicAdd((unsigned long long*)&sp.counters[5], 1ull);
+            sp.pull_jobs[job] = make_int4(k, ra, rb, d);
+          }
+        }
+        __stcg(rm_new + i, d);
+      }
     }
     for (long long r = gt; r < pd.cap; r += GT) __stcg(pd.refcnt + r, 0);
-    if (gt == 0) { __stcg(pd.ctr, 1); __stcg(pd.ctr + 1, 0); }
   }
   for (int sl = threadIdx.x; sl < ns; sl += PMDI_NT) T.lw_s[sl] = 1.0;  // logweight .= 1.0 (src/pmdi.jl:319)
+  if (!pool_gsync(sp, sm)) return false;
+  // ---- A2: pull the reserved rows; the other children of a remote ancestor share its first child's map
+  if (sp.R > 1) {
+    const long long njobs = __ldcg(&sp.counters[5]);
+    const long long gw = gt >> 5, GWp = GT >> 5;
+    for (long long job = gw; job < njobs; job += GWp) {
+      const int4 jb = __ldcg(sp.pull_jobs + job);
+      pool_row_pull(sp, jb.x, sp.peer_delta[jb.y], jb.z, jb.w);
+    }
+    if (gt == 0) sp.counters[3] += njobs;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      int* rm_new = sp.pd[k].rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+      for (long long i = gt; i < (long long)Ps * N; i += GT) {
+        const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
+        const int a1 = ldcg_i32(anc + sp.slot0 + slot);
+        if ((a1 - 1) / Ps == sp.rank) continue;
+        int f = slot;
+        while (f > 0 && ldcg_i32(anc + sp.slot0 + f - 1) == a1) --f;
+        if (f != slot) __stcg(rm_new + i, ldcg_i32(rm_new + (size_t)f * N + m));
+      }
+    }
+  }
+  if (gt == 0)
+    for (int k = 0; k < K; ++k) { __stcg(sp.pd[k].ctr, 1); __stcg(sp.pd[k].ctr + 1, 0); }  // the lists are rebuilt below
   if (!pool_gsync(sp, sm)) return false;
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
@@ -570,7 +679,9 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
     }
     if (gt == 0) { __stcg(pd.refcnt + pd.cap - 1, POOL_BIG_REF); pd.live[0] = pd.cap - 1; }
   }
-  if (!pool_gsync(sp, sm)) return false;
+  if (gt == 0) sp.counters[5] = 0;
+  // no rank may hand out a freed row while a peer is still pulling from it
+  if (!pool_xsync(sp, sm)) return false;
   if (gt == 0 && st + 1 < sp.steps) {
     long long u = 0;
     for (int k = 0; k < K; ++k) u += ldcg_i32(sp.pd[k].ctr);
@@ -581,6 +692,54 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
   pool_load_units(sp, sm, T, ns);  // the new row maps; the units' reserved rows were freed with the dead rows
   __syncthreads();
   return !sm.fail;
+}
+
+// ---- cross-rank ESS (R > 1).  After B2(t) one warp of CTA 0 folds this rank's CTA partials into
+// one (max, sum w, sum w^2) and pushes it, tagged with the step, to every rank; the ranks combine
+// the R rank partials before P(t+1) - a whole evaluation phase later.
+__device__ __forceinline__ void pool_push_rank_partial(const SweepParams& sp, int t) {
+  const int lane = threadIdx.x & 31, par = t & 1;
+  double mxv, num, den;
+  pool_combine(sp.ess_part + (size_t)par * sp.G * 3, sp.G, 3, mxv, num, den);
+  if (lane == 0) {
+    double* mine = sp.rank_part + ((size_t)par * sp.R + sp.rank) * 4;
+#pragma unroll 1
+    for (int r = 0; r < sp.R; ++r) {
+      double* e = on_rank(sp, mine, r);
+      __stcg(e, mxv); __stcg(e + 1, num); __stcg(e + 2, den);
+    }
+    __threadfence_system();
+#pragma unroll 1
+    for (int r = 0; r < sp.R; ++r) {
+      unsigned long long* f = (unsigned long long*)(on_rank(sp, mine, r) + 3);
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)(t + 1)) : "memory");
+    }
+  }
+}
+// one warp: wait for every rank's partial of step t, then calc_ESS over them (same bits on every rank)
+__device__ __noinline__ void pool_resolve_ranks(const SweepParams& sp, PoolSmem& sm, int t) {
+  const int lane = threadIdx.x & 31, par = t & 1;
+  const double* base = sp.rank_part + (size_t)par * sp.R * 4;
+  if (lane < sp.R) {
+    const unsigned long long* f = (const unsigned long long*)(base + (size_t)lane * 4 + 3);
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+    while (ld_acquire_sys_u64(f) < (unsigned long long)(t + 1)) {
+      if (((++spins) & 0x3ffu) == 0) {
+        if (__ldcg(sp.err) != 0) break;
+        if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); break; }
+      }
+    }
+  }
+  __syncwarp();
+  double mxv, num, den;
+  pool_combine(base, sp.R, 4, mxv, num, den);
+  if (lane == 0) {
+    const bool res = (num * num) / den <= 0.5 * (double)sp.P;  // src/pmdi.jl:317
+    sm.res_mx = mxv;
+    sm.res_flag = res ? 1 : 0;
+    if (!res && blockIdx.x == 0) sp.ev_of_step[t] = -1;
+  }
 }
 
 extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __grid_constant__ SweepParams sp) {
@@ -623,7 +782,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
   if (tid < PMDI_MAX_K) { sm.rows_eval[tid] = 0; sm.rows_ref[tid] = 0; }
   if (tid < 8) sm.tacc[tid] = 0;
   if (tid == 0) {
-    sm.res_flag = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.epoch = 0; sm.res_mx = 0.0;
+    sm.res_flag = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.epoch = 0; sm.xepoch = 0; sm.res_mx = 0.0;
     for (int b = 0; b < sp.obs_ring; ++b) mbar_init(&sm.obs_bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     pool_snapshot(sp, sm, 0);
@@ -654,6 +813,10 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
     if (t > 0) {
       if (tid == 0) pool_issue_obs(sp, t - 1 + sp.obs_ring, xring, sm.obs_bar);  // x[t-1] is dead: its slot refills
       pool_duties(sp, T, nu, par ^ 1);
+      if (sp.R > 1) {  // the ranks' partials of step t-1 have had E(t) to arrive
+        if (warp == NW - 1) pool_resolve_ranks(sp, sm, t - 1);
+        __syncthreads();
+      }
       if (sm.res_flag) {
         if (!pool_resample(sp, sm, T, ns, t - 1, s_tmp)) return;
         PHASE_MARK(6)
@@ -667,7 +830,9 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
     PHASE_MARK(0)
     // ---- R(t)
     pool_resolve_units(sp, sm, T, nu, par);
-    if (warp == NW - 1) {  // calc_ESS (src/misc.jl:15-25), same bits in every CTA; the last warp has the fewest items
+    if (sp.R > 1) {
+      if (cta == 0 && warp == NW - 1) pool_push_rank_partial(sp, t);
+    } else if (warp == NW - 1) {  // calc_ESS (src/misc.jl:15-25), same bits in every CTA; the last warp has the fewest items
       double mxv, num, den;
       pool_combine(sp.ess_part + (size_t)par * G * 3, G, 3, mxv, num, den);
       if (lane == 0) {
@@ -686,6 +851,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
   }
   // ---- after the last observation: its bookkeeping (cluster sizes), and its ESS test
   pool_duties(sp, T, nu, (steps - 1) & 1);
+  if (sp.R > 1 && warp == NW - 1) pool_resolve_ranks(sp, sm, steps - 1);
   __syncthreads();
   const int final_res = sm.res_flag;
   if (final_res && !pool_resample(sp, sm, T, ns, steps - 1, s_tmp)) return;
@@ -694,9 +860,12 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
     atomicAdd(sp.rows_ref + tid, (unsigned long long)sm.rows_ref[tid]);
   }
   if (cta == 0)  // after a final resampling all log-weights are 1.0 (src/pmdi.jl:319)
-    for (int p = tid; p < sp.P; p += PMDI_NT) sp.lw_out[p] = final_res ? 1.0 : __ldcg(sp.lw + p);
+    for (int p = tid; p < sp.P; p += PMDI_NT)
+      sp.lw_out[p] = final_res ? 1.0 : __ldcg(on_rank(sp, sp.lw + p, p / sp.Ps));
   if (timing && tid < 8) sp.phase_ns[(size_t)cta * 8 + tid] = sm.tacc[tid] / NW;
   if (cta == 0 && tid == 0) sp.counters[2] = sm.ev;
+  // the peers' stores into this rank's allocation log have landed before the finish kernel reads it
+  if (sp.R > 1) pool_xsync(sp, sm);
 #undef PHASE_MARK
 }
 
