@@ -19,7 +19,7 @@ __global__ void k_init_rows(DsDev ds, long long rows) {
   } else {
     for (long long i = t0; i < rows * ds.Dp; i += stride) ds.S[i] = 0;
   }
-  for (long long i = t0; i < rows * ds.J; i += stride) { ds.aux[i] = 0.0; ds.part[i] = 0.0; }
+  for (long long i = t0; i < rows * ds.J; i += stride) { ds.aux[i] = 0.0; if (ds.part) ds.part[i] = 0.0; }
   for (long long i = t0; i < rows; i += stride) ds.n[i] = 0;
 }
 
@@ -248,8 +248,9 @@ __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
       const PoolDev& pd = sp.pd[k];
       const int base = j * PMDI_FB + 2 * lane;
       const int nits = min(PMDI_FB / PMDI_WF, (ds.Dp - j * PMDI_FB) / PMDI_WF);
-      v = cat_eval_pool(pd.cw + ((size_t)row * ds.Dp + base) * pd.wpf, pd.wpf, pd.fpw,
-                        (unsigned)__cvta_generic_to_shared(xs_raw) + base * 4u, nits);
+      double unused;
+      v = cat_block(pd.cw + ((size_t)row * ds.Dp + base) * pd.wpf, 0, pd.wpf, pd.fpw, nits, 0, 0u,
+                    (unsigned)__cvta_generic_to_shared(xs_raw) + base * 4u, &unused);
     }
     else if (ds.type == T_CATEGORICAL) v = cat_eval_block(ds, row, j, (const int*)xs_raw, lane);
     else v = nb_eval_block(ds, row, j, n, (const int*)xs_raw, lane, sp.lf_glob, sp.lf_glob_T);

@@ -80,12 +80,13 @@ struct Dataset {
   int cap = 0, wpf = 1, fpw = 4;
   DevBuf<unsigned long long> cw;
   DevBuf<int> p_refcnt, p_chosen, p_dst, p_neval, p_live, p_free, p_rowmap, p_ctr;
+  DevBuf<double> p_lp;
   void release() {
     x.release(); xq.release(); d_flag.release(); rc.release(); d_nlevels.release();
     mu.release(); lamn.release(); sum.release(); beta.release(); part.release(); aux.release();
     cnt.release(); S.release(); n.release(); cw.release();
     p_refcnt.release(); p_chosen.release(); p_dst.release(); p_neval.release(); p_live.release();
-    p_free.release(); p_rowmap.release(); p_ctr.release();
+    p_free.release(); p_rowmap.release(); p_ctr.release(); p_lp.release();
   }
 };
 
@@ -158,7 +159,7 @@ void fill_dsdev(pmdi_ctx* c, int k, DsDev& d) {
   d.x = s.x.p; d.flag = s.d_flag.p; d.rc = s.rc.p;
   d.xstage = (s.type != T_GAUSSIAN && nflag != s.D) ? (const void*)s.xq.p : (const void*)s.x.p;
   d.mu = s.mu.p; d.lamn = s.lamn.p; d.sum = s.sum.p; d.beta = s.beta.p;
-  d.cnt = s.cnt.p; d.S = s.S.p; d.part = s.part.p; d.aux = s.aux.p; d.n = s.n.p;
+  d.cnt = s.cnt.p; d.S = s.S.p; d.part = c->engine ? nullptr : s.part.p; d.aux = s.aux.p; d.n = s.n.p;
 }
 
 void fill_pooldev(pmdi_ctx* c, int k, PoolDev& d) {
@@ -167,6 +168,7 @@ void fill_pooldev(pmdi_ctx* c, int k, PoolDev& d) {
   d.cap = s.cap; d.wpf = s.wpf; d.fpw = s.fpw;
   d.refcnt = s.p_refcnt.p; d.chosen = s.p_chosen.p; d.dst = s.p_dst.p; d.n_eval = s.p_neval.p;
   d.live = s.p_live.p; d.freelist = s.p_free.p; d.rowmap = s.p_rowmap.p; d.ctr = s.p_ctr.p; d.cw = s.cw.p;
+  d.lp = s.p_lp.p;
 }
 
 // x-independent row constants by cluster size n:
@@ -259,7 +261,7 @@ int build_layout(pmdi_ctx* c) {
   const size_t o_lw = take(sizeof(double) * (size_t)c->P);
   const size_t o_log = take((size_t)c->n * K * c->P);  // at most n_obs observation steps
   const size_t o_rankp = take(sizeof(double) * 2 * 8 * 4);
-  struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n, cw, refcnt, chosen, dst, neval, live, free_, rowmap, ctr; };
+  struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n, cw, refcnt, chosen, dst, neval, live, free_, rowmap, ctr, lp; };
   std::vector<Off> offs(K);
   for (int k = 0; k < K; ++k) {
     Dataset& s = c->ds[k];
@@ -279,11 +281,12 @@ int build_layout(pmdi_ctx* c) {
     } else {
       o.S = take(8 * rows * s.Dp);
     }
-    o.part = take(8 * rows * s.J); o.aux = take(8 * rows * s.J); o.n = take(4 * rows);
+    o.part = take(c->engine ? 8 : 8 * rows * s.J); o.aux = take(8 * rows * s.J); o.n = take(4 * rows);
     if (c->engine) {
       s.cap = (int)rows;
       o.refcnt = take(4 * rows); o.chosen = take(8 * rows); o.dst = take(8 * rows); o.neval = take(4 * rows);
       o.live = take(4 * rows); o.free_ = take(4 * rows); o.rowmap = take(8 * (size_t)c->Ps * c->N); o.ctr = take(64);
+      o.lp = take(8 * rows);
     }
   }
   if (c->arena) { cudaFree(c->arena); c->arena = nullptr; }
@@ -304,6 +307,7 @@ int build_layout(pmdi_ctx* c) {
       s.p_refcnt.view(A + o.refcnt, rows); s.p_chosen.view(A + o.chosen, 2 * rows); s.p_dst.view(A + o.dst, 2 * rows);
       s.p_neval.view(A + o.neval, rows); s.p_live.view(A + o.live, rows); s.p_free.view(A + o.free_, rows);
       s.p_rowmap.view(A + o.rowmap, 2 * (size_t)c->Ps * c->N); s.p_ctr.view(A + o.ctr, 16);
+      s.p_lp.view(A + o.lp, rows);
     }
     if (s.type == T_GAUSSIAN) {
       s.mu.view(A + o.mu, rows * s.Dp); s.lamn.view(A + o.lamn, rows * s.Dp);
@@ -313,7 +317,7 @@ int build_layout(pmdi_ctx* c) {
     } else {
       s.S.view(A + o.S, rows * s.Dp);
     }
-    s.part.view(A + o.part, rows * s.J); s.aux.view(A + o.aux, rows * s.J); s.n.view(A + o.n, rows);
+    s.part.view(A + o.part, c->engine ? 1 : rows * s.J); s.aux.view(A + o.aux, rows * s.J); s.n.view(A + o.n, rows);
     DsDev d;
     fill_dsdev(c, k, d);
     if (!(c->engine && s.type == T_CATEGORICAL)) k_init_rows<<<c->n_sm * 4, 256, 0, c->stream>>>(d, rows);
@@ -353,8 +357,8 @@ int assign_units(pmdi_ctx* c) {
   if (c->engine) {
     // pool engine: observation ring (2..4 deep) | lf | proposal scratch | Pi | lw | inc | unit tables
     const long long tables = (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 + MS * 8 + MU * 8 +
-                             (MU * 10 + MS + MU * N) * 4 + 64;
-    const long long budget = (long long)dev_smem - 4096 - tables;
+                             (MU * 11 + MS + MU * N) * 4 + 64;
+    const long long budget = (long long)dev_smem - 8192 - tables;  // static shared memory: the parameter block, PoolSmem
     int ring = PMDI_OBS_RING;
     while (ring > 2 && (long long)ring * c->sm_x_bytes + std::min<long long>((long long)c->lf_want * 8, 64 * 1024) > budget) --ring;
     if ((long long)ring * c->sm_x_bytes + (c->lf_want > 0 ? 2048 : 0) > budget)
@@ -367,6 +371,7 @@ int assign_units(pmdi_ctx* c) {
     c->item_cap = 0;
     c->dyn_smem = (size_t)((long long)ring * c->sm_x_bytes + (long long)c->lf_T * 8 + tables);
     CK(cudaFuncSetAttribute(k_sweep_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+    CK(cudaFuncSetAttribute(k_sweep_pool_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
   } else {
     // dense engine: 4 observation buffers | lf | proposal scratch | Pi | lw | inc | part x2 | items x2 | unit tables
     const long long fixed = 4LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 +
@@ -420,7 +425,8 @@ int fill_params(pmdi_ctx* c) {
   // warps have work (cfg2, 6 units: 1-2 blocks best, 3 already +3 %); with many units a whole row per item
   // is best (cfg4, 14 units: 8 blocks 9 % faster than 2) - profiles/r01_k_sweep_cfg4.md.  PMDI_QB overrides.
   sp.qb = getenv("PMDI_QB") ? std::max(1, atoi(getenv("PMDI_QB"))) : (c->max_units >= 11 ? std::max(2, c->Jmax) : 2);
-  if (c->engine) sp.qb = getenv("PMDI_QB") ? std::max(1, atoi(getenv("PMDI_QB"))) : 0;  // pool: 0 = chosen per step
+  sp.jq = 1;
+  while (sp.jq < c->Jmax && sp.jq < PMDI_NT / 32) sp.jq *= 2;
   return 0;
 }
 
@@ -800,7 +806,9 @@ int pmdi_sweep_run(pmdi_ctx* c) {
     k_pool_init<<<K, 1024, 0, st>>>(sp);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, st));
-    CK(cudaLaunchCooperativeKernel((const void*)k_sweep_pool, dim3(c->G), dim3(PMDI_NT), args, c->dyn_smem, st));
+    const bool dbg = (c->sweep_flags & (PMDI_SWEEP_DEBUG | PMDI_SWEEP_TIME_PHASES)) || sp.trace;
+    CK(cudaLaunchCooperativeKernel(dbg ? (const void*)k_sweep_pool_dbg : (const void*)k_sweep_pool, dim3(c->G), dim3(PMDI_NT), args,
+                                   c->dyn_smem, st));
   } else {
     k_broadcast<<<c->n_sm * 8, 256, 0, st>>>(sp);
     k_empty_lp<<<sp.steps, 256, c->sm_x_bytes, st>>>(sp, c->lp_empty.p);

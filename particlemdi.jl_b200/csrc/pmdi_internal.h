@@ -62,6 +62,7 @@ struct PoolDev {
   int* rowmap;       /* [2][Ps][N] by resampling-event parity: label -> row of a particle slot */
   int* ctr;          /* [0] live rows, [1] free rows                                          */
   unsigned long long* cw; /* [cap][Dp][wpf] packed categorical counts                          */
+  double* lp;        /* [cap] this step's predictive of every live row (E phase -> P phase)       */
 };
 
 struct SweepParams {
@@ -111,7 +112,8 @@ struct SweepParams {
   const int* cta_units;   /* k << 24 | slot                                   */
   int max_units, sm_x_bytes;
   int lf_T, item_cap;   /* log-factorial entries in smem; capacity of the per-step item queue */
-  int qb;               /* 256-feature blocks per plain work item            */
+  int qb;               /* 256-feature blocks per plain work item (dense engine) */
+  int jq;               /* pool engine: warps per row task = blocks per row rounded up to a power of two, <= 16 */
   const double* lf_glob;  /* log-factorial table in HBM [lf_glob_T]; its first lf_T entries are staged in smem */
   int lf_glob_T;
   unsigned* bar;          /* grid barrier arrival counter (64-bit, 16 bytes reserved) */

@@ -11,42 +11,68 @@
 // predictive do not depend on how many particles share it.
 //
 // Per observation step t the grid runs two phases separated by grid barriers:
-//   E(t)  every live row's predictive of x[t]  (warps take (row, feature-block) items round-robin
-//         over the whole grid).  A row that was chosen at step t-1 gets x[t-1] added in the same
+//   E(t)  every live row's predictive of x[t].  A CTA takes rows round-robin; the row's 256-feature
+//         blocks go to the CTA's warps, the block partials meet in shared memory and ONE number per
+//         row (lp[row]) goes to HBM.  A row that was chosen at step t-1 gets x[t-1] added in the same
 //         pass: in place, or - split - source row read once, fresh row written, both evaluated.
 //   -- B1 --
-//   P(t)  per (dataset, particle) unit, one warp: gather the lp of the particle's N labels through
-//         its row map, softmax-cdf, draw, weight increment (src/pmdi.jl:223-265); count the
-//         choosers of the chosen row; the first chooser reserves a row for a possible split.  The
-//         K-th proposal of a particle folds its log-weight with the Phi coupling (src/misc.jl:50-59);
-//         the CTA's last particle publishes the CTA's (max, sum w, sum w^2).
+//   P(t)  per (dataset, particle) unit, one warp: gather lp of the particle's N labels through its
+//         row map, softmax-cdf, draw, weight increment (src/pmdi.jl:223-265); count the choosers of
+//         the chosen row; the first chooser reserves a row for a possible split.  The K-th proposal
+//         of a particle folds its log-weight with the Phi coupling (src/misc.jl:50-59); the CTA's
+//         last particle publishes the CTA's (max, sum w, sum w^2).
 //   -- B2 --
-//   R(t)  choosers learn the row their label now maps to (tot == refcnt: in place); one warp per
-//         CTA evaluates calc_ESS (src/misc.jl:15-25) - then straight into E(t+1).
+//   R(t)  choosers learn the row their label now maps to (tot == refcnt: in place); CTA 0 evaluates
+//         calc_ESS (src/misc.jl:15-25) and attaches the decision to its arrival at B1(t+1) - then
+//         straight into E(t+1).
 // The ESS decision of step t is needed only before P(t+1): evaluations never depend on it (rows
 // do not change under resampling), so with several GPUs the cross-rank exchange of the ESS
 // partials is off the dependent chain; it has the whole of E(t+1) to arrive.
+//
+// The sweep is a chain of ~2 x steps dependent grid phases, each a few microseconds: it is bound by
+// latency, and on this machine latency means INSTRUCTION FETCH as much as memory (32 KB of L1.5
+// instruction cache per SM, a miss is an L2 round trip).  Hence: one block operator per cluster
+// type (pool_types.cuh), debug capture / tracing / phase timing compiled into a separate kernel
+// instantiation, the parameter block in shared memory, rare paths (resampling) out of line.
 #pragma once
 #include "pool_types.cuh"
 #include "sweep_kernel.cuh"
 
 #define POOL_BIG_REF (1 << 30)
+#define POOL_NW (PMDI_NT / 32)
+#define POOL_FLAG_SHIFT 44  // grid counter: arrivals in the low 44 bits, resampling decisions above
+#define POOL_ARRIVE_MASK ((1ull << POOL_FLAG_SHIFT) - 1ull)
 
 struct PoolSmem {
   unsigned long long obs_bar[PMDI_OBS_RING];
   unsigned long long epoch;    // local grid-barrier arrivals expected so far
   unsigned long long xepoch;   // cross-rank barrier arrivals expected so far (one per rank)
   double res_mx;
+  double red[2][2][32];        // [row-iteration parity][updated or plain / split source][block] partials
   int res_flag;                // the last resolved step resamples
+  int res_next;                // CTA 0: the decision to attach to the next B1 arrival
   int fail;
   int ev;                      // resampling events so far
   int pdone;                   // particles of this CTA folded this step
-  int U[2][PMDI_MAX_K];        // by step parity: live rows covered by the step's item list
-  int qb[2][PMDI_MAX_K];       // by step parity: 256-feature blocks per item
-  int ibase[2][PMDI_MAX_K + 1];  // by step parity: first item of each dataset
+  int U[2][PMDI_MAX_K];        // by step parity: live rows of each dataset covered by the E phase
+  int rbase[2][PMDI_MAX_K + 1];  // by step parity: first row task of each dataset
   unsigned rows_eval[PMDI_MAX_K], rows_ref[PMDI_MAX_K];
   unsigned long long tacc[8];
+  int tr_n[POOL_NW];
 };
+
+// optional per-warp event trace of one CTA and one step (PMDI_TRACE_STEP): tag << 48 | clock64; stores only
+__device__ __forceinline__ void pool_trace(const SweepParams& sp, PoolSmem& sm, int step, unsigned tag) {
+  if (sp.trace && step == sp.trace_step && (int)blockIdx.x == sp.trace_cta && (threadIdx.x & 31) == 0) {
+    const int w = threadIdx.x >> 5;
+    const int n = ++sm.tr_n[w];
+    if (n < 128) {
+      sp.trace[w * 128 + n] = ((unsigned long long)tag << 48) | (clock64() & 0xFFFFFFFFFFFFull);
+      sp.trace[w * 128] = n;
+    }
+  }
+}
+#define TRACE(step_, tag_) if constexpr (DBG) pool_trace(sp, sm, (step_), (tag_));
 
 struct PoolTables {
   double* lf;      // [lf_T]
@@ -64,36 +90,44 @@ struct PoolTables {
   int* u_dd;       // [MU] duty: destination row
   int* u_dtot;     // [MU] duty: number of choosers
   int* u_spare;    // [MU] row reserved by the unit for the next split it leads
+  int* u_ks;       // [MU] dataset | local slot index << 8 of the unit
   int* rm_s;       // [MU][N] the units' row maps (copy of rowmap[ev & 1] rows of the owned slots)
 };
 
-// local grid barrier (this GPU's CTAs), all threads
-// (sys: this CTA's peer stores are made visible system-wide before it arrives - the cross-rank barrier)
-__device__ __noinline__ bool pool_gsync(const SweepParams& sp, PoolSmem& sm, bool sys = false) {
+// Local grid barrier (this GPU's CTAs), all threads.  b1: the barrier after an E phase - CTA 0 attaches
+// its ESS decision to its arrival, everybody reads it off the counter it polls anyway (R == 1).
+// sys: this CTA's peer stores are made visible system-wide before it arrives (cross-rank barrier).
+__device__ __noinline__ bool pool_gsync(const SweepParams& sp, PoolSmem& sm, int b1 = 0, bool sys = false) {
   __syncthreads();
   if (threadIdx.x == 0) {
     sm.epoch += (unsigned long long)sp.G;
+    unsigned long long inc = 1ull;
+    if (b1 && blockIdx.x == 0 && sm.res_next) inc += 1ull << POOL_FLAG_SHIFT;
     if (sys) __threadfence_system(); else __threadfence();
-    atomicAdd((unsigned long long*)sp.bar, 1ull);
-    const unsigned long long t0 = globaltimer_ns();
-    unsigned spins = 0;
-    while (ld_acquire_u64((const unsigned long long*)sp.bar) < sm.epoch) {
-      if (((++spins) & 0x3ffu) == 0) {
-        if (__ldcg(sp.err) != 0) { sm.fail = 1; break; }
-        if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); sm.fail = 1; break; }
+    atomicAdd((unsigned long long*)sp.bar, inc);
+    unsigned long long v = ld_acquire_u64((const unsigned long long*)sp.bar);
+    if ((v & POOL_ARRIVE_MASK) < sm.epoch) {
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned spins = 0;
+#pragma unroll 1
+      while (((v = ld_acquire_u64((const unsigned long long*)sp.bar)) & POOL_ARRIVE_MASK) < sm.epoch) {
+        if (((++spins) & 0x3ffu) == 0) {
+          // a CTA that failed has set sp.err before leaving: the others see it here
+          if (__ldcg(sp.err) != 0) { sm.fail = 1; break; }
+          if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); sm.fail = 1; break; }
+        }
       }
     }
-    __threadfence();
-    if (__ldcg(sp.err) != 0) sm.fail = 1;  // every CTA leaves at the same barrier
+    if (b1) sm.res_flag = (((v >> POOL_FLAG_SHIFT) - (unsigned long long)sm.ev) & 0xFFFFFull) != 0ull;
   }
   __syncthreads();
   return sm.fail == 0;
 }
 
 // barrier over the CTAs of ALL ranks: local barrier, one arrival per rank on every rank's counter
-// (NVLink peer atomics), local barrier.  Resampling only.
+// (NVLink peer atomics), local barrier.  Resampling and the end of the sweep only.
 __device__ __noinline__ bool pool_xsync(const SweepParams& sp, PoolSmem& sm) {
-  if (!pool_gsync(sp, sm, sp.R > 1)) return false;
+  if (!pool_gsync(sp, sm, 0, sp.R > 1)) return false;
   if (sp.R > 1) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
       unsigned long long* xbar = (unsigned long long*)sp.bar + 1;
@@ -103,6 +137,7 @@ __device__ __noinline__ bool pool_xsync(const SweepParams& sp, PoolSmem& sm) {
       for (int r = 0; r < sp.R; ++r) atomicAdd_system(on_rank(sp, xbar, r), 1ull);
       const unsigned long long t0 = globaltimer_ns();
       unsigned spins = 0;
+#pragma unroll 1
       while (ld_acquire_sys_u64(xbar) < sm.xepoch) {
         if (((++spins) & 0x3ffu) == 0) {
           if (__ldcg(sp.err) != 0) break;
@@ -139,160 +174,121 @@ __device__ __noinline__ void pool_issue_obs(const SweepParams& sp, int step, uns
   }
 }
 
-// item list of the E phase of step `st` (parity b): live-row counts as they are now (stable during
-// the P phase before it), blocks per item so that the grid's warps all get work.  One thread.
-__device__ __noinline__ void pool_snapshot(const SweepParams& sp, PoolSmem& sm, int b) {
-  const int GW = sp.G * (PMDI_NT / 32);
-  long long W = 0;
-  for (int k = 0; k < sp.K; ++k) { sm.U[b][k] = ldcg_i32(sp.pd[k].ctr); W += sm.U[b][k]; }
-  const int f = (int)max(1ll, min((long long)sp.Jmax, (long long)GW / max(W, 1ll)));
-  int base = 0;
-  for (int k = 0; k < sp.K; ++k) {
-    const int J = sp.ds[k].J;
-    const int pieces = min(J, f);
-    const int qb = sp.qb > 0 ? min(J, sp.qb) : (J + pieces - 1) / pieces;
-    sm.qb[b][k] = qb;
-    sm.ibase[b][k] = base;
-    base += sm.U[b][k] * ((J + qb - 1) / qb);
-  }
-  sm.ibase[b][sp.K] = base;
-}
-
-// plain predictive of blocks [j0, j1) of row r (no pending add)
-__device__ __forceinline__ double pool_eval_plain(const SweepParams& sp, int k, long long r, int j0, int j1, int n,
-                                                  const unsigned char* xs, const double* lf, int lane) {
-  const DsDev& ds = sp.ds[k];
-  const int base = j0 * PMDI_FB + 2 * lane;
-  const int nits = (min(ds.Dp, j1 * PMDI_FB) - j0 * PMDI_FB) / PMDI_WF;
-  if (ds.type == T_GAUSSIAN)
-    return gauss_eval_raw(ds.mu + r * ds.Dp + base, ds.lamn + r * ds.Dp + base, ds.aux + r * ds.J + j0,
-                          ds.all_on ? nullptr : ds.flag + base,
-                          (unsigned)__cvta_generic_to_shared(xs + ds.x_off) + base * 8u, nits, j1 - j0, n, lane);
-  if (ds.type == T_NEGBINOM)
-    return nb_eval_raw(ds.S + r * ds.Dp + base, ds.aux + r * ds.J + j0,
-                       (unsigned)__cvta_generic_to_shared(xs + ds.x_off) + base * 4u, nits, j1 - j0, n,
-                       (unsigned)__cvta_generic_to_shared(lf), sp.lf_T, lane);
-  const PoolDev& pd = sp.pd[k];
-  return cat_eval_pool(pd.cw + ((size_t)r * ds.Dp + base) * pd.wpf, pd.wpf, pd.fpw,
-                       (unsigned)__cvta_generic_to_shared(xs + ds.x_off) + base * 4u, nits);
-}
-
-// cluster_add!(x_prev) src -> dst of blocks [j0, j1) + predictive of x_cur; n = size after the add.
-// Returns the updated row's partial; with SPLIT, *v_src = the source row's partial.
-template <bool SPLIT>
-__device__ __forceinline__ double pool_eval_cow(const SweepParams& sp, int k, long long src, long long dst, int j0,
-                                                int j1, int n, const unsigned char* xp, const unsigned char* xc,
-                                                const double* lf, int lane, double* v_src) {
-  const DsDev& ds = sp.ds[k];
-  double vd = 0.0, vs = 0.0;
+// row tasks of the E phase of the step with parity b: the live rows as they are now (stable during
+// the P phase before it).  One warp.
+__device__ __forceinline__ void pool_snapshot(const SweepParams& sp, PoolSmem& sm, int b) {
+  const int lane = threadIdx.x & 31;
+  if (lane < sp.K) sm.U[b][lane] = ldcg_i32(sp.pd[lane].ctr);
+  __syncwarp();
+  if (lane == 0) {
+    int base = 0;
 #pragma unroll 1
-  for (int j = j0; j < j1; ++j) {
-    const int q0 = j * PMDI_FB;
-    const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
-    const int base = q0 + 2 * lane;
-    double es = 0.0;
-    if (ds.type == T_GAUSSIAN) {
-      const long long so = src * ds.Dp + base, dof = dst * ds.Dp + base;
-      vd += gauss_cow_block<SPLIT>(ds.sum + so, ds.beta + so, ds.mu + so, ds.lamn + so, ds.sum + dof,
-                                   ds.beta + dof, ds.mu + dof, ds.lamn + dof, ds.aux + dst * ds.J + j,
-                                   ds.flag + base, nit, n, (const double*)(xp + ds.x_off) + base,
-                                   (const double*)(xc + ds.x_off) + base, &es);
-      if (SPLIT) vs += ldcg_f64(ds.aux + src * ds.J + j) - (0.5 * (double)(n - 1) + 1.0) * es;
-    } else if (ds.type == T_NEGBINOM) {
-      vd += nb_cow_block<SPLIT>(ds.S + src * ds.Dp + base, ds.S + dst * ds.Dp + base, ds.aux + dst * ds.J + j, nit, n,
-                                (unsigned)__cvta_generic_to_shared(xp + ds.x_off) + base * 4u,
-                                (unsigned)__cvta_generic_to_shared(xc + ds.x_off) + base * 4u,
-                                (unsigned)__cvta_generic_to_shared(lf), sp.lf_T, &es);
-      if (SPLIT) vs += ldcg_f64(ds.aux + src * ds.J + j) + es;
-    } else {
-      const PoolDev& pd = sp.pd[k];
-      vd += cat_cow_block<SPLIT>(pd.cw + ((size_t)src * ds.Dp + base) * pd.wpf,
-                                 pd.cw + ((size_t)dst * ds.Dp + base) * pd.wpf, pd.wpf, pd.fpw, nit,
-                                 (unsigned)__cvta_generic_to_shared(xp + ds.x_off) + base * 4u,
-                                 (unsigned)__cvta_generic_to_shared(xc + ds.x_off) + base * 4u, &es);
-      if (SPLIT) vs += es;
-    }
+    for (int k = 0; k < sp.K; ++k) { sm.rbase[b][k] = base; base += sm.U[b][k]; }
+    sm.rbase[b][sp.K] = base;
   }
-  if (SPLIT) *v_src = vs;
-  return vd;
+  __syncwarp();
 }
 
 // E phase of step `st`: predictive of x[st] for every live row; rows chosen at step st-1 (pending
-// parity pp = (st-1)&1, or -1 at the first step) get x[st-1] added on the way.
-__device__ __noinline__ void pool_eval_phase(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int st, int pp,
-                                             unsigned char* xring, int& obs_ok) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, NW = PMDI_NT / 32;
+// parity pp = (st-1)&1, or -1 at the first step) get x[st-1] added on the way.  The CTA takes
+// `rpc` rows at a time (rpc = 16 warps / jq, jq = blocks per row rounded up to a power of two):
+// warp w works on block w % jq (+ jq, ...) of row task w / jq, the partials meet in shared memory.
+__device__ __noinline__ void pool_eval_rows(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int st, int pp,
+                                            unsigned char* xring, int& obs_ok) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = st & 1, K = sp.K;
-  const int GW = sp.G * NW, gw = warp * sp.G + (int)blockIdx.x;
-  const int total = sm.ibase[b][K];
-  const unsigned char* xc = xring + (size_t)(st % sp.obs_ring) * sp.sm_x_bytes;
-  const unsigned char* xp = xring + (size_t)((st + sp.obs_ring - 1) % sp.obs_ring) * sp.sm_x_bytes;
+  const int jq = sp.jq, rpc = POOL_NW / jq;
+  const int sub = warp / jq, wj = warp - sub * jq;
+  const int total = sm.rbase[b][K];
+  const unsigned xc = (unsigned)__cvta_generic_to_shared(xring + (size_t)(st % sp.obs_ring) * sp.sm_x_bytes);
+  const unsigned xp = (unsigned)__cvta_generic_to_shared(xring + (size_t)((st + sp.obs_ring - 1) % sp.obs_ring) * sp.sm_x_bytes);
+  int buf = 0;
 #pragma unroll 1
-  for (int idx = gw; idx < total; idx += GW) {
-    if (obs_ok < st) {  // x[st] has landed in the ring (x[st-1] was waited for one step ago)
-      if (lane == 0) {
+  for (int base = (int)blockIdx.x * rpc; base < total; base += sp.G * rpc, buf ^= 1) {
+    const int idx = base + sub;
+    const bool active = sub < rpc && idx < total;
+    int k = 0, c = 0, d = 0, mode = 0, nc = 0;
+    if (active) {
 #pragma unroll 1
-        for (int s = max(obs_ok + 1, st - 1); s <= st; ++s)
-          while (!mbar_try_wait(&sm.obs_bar[s % sp.obs_ring], (unsigned)(s / sp.obs_ring) & 1u)) {}
+      while (k + 1 < K && idx >= sm.rbase[b][k + 1]) ++k;
+      const DsDev& ds = sp.ds[k];
+      const PoolDev& pd = sp.pd[k];
+      if (wj < ds.J) {
+        if (obs_ok < st) {  // x[st] has landed in the ring (x[st-1] was waited for one step ago)
+          if (lane == 0) {
+#pragma unroll 1
+            for (int s = max(obs_ok + 1, st - 1); s <= st; ++s)
+#pragma unroll 1
+              while (!mbar_try_wait(&sm.obs_bar[s % sp.obs_ring], (unsigned)(s / sp.obs_ring) & 1u)) {}
+          }
+          __syncwarp();
+          obs_ok = st;
+        }
+        c = ldcg_i32(pd.live + (idx - sm.rbase[b][k]));
+        int tot = 0;  // the row's bookkeeping words in one round trip
+        nc = ldcg_i32(ds.n + c);
+        const int rf = ldcg_i32(pd.refcnt + c);
+        d = c;
+        if (pp >= 0) { tot = ldcg_i32(pd.chosen + (size_t)pp * pd.cap + c); d = ldcg_i32(pd.dst + (size_t)pp * pd.cap + c); }
+        // every reference chose it: in place (src/pmdi.jl:284-286); some did: split (:288-309)
+        mode = tot == 0 ? 0 : (tot == rf ? 1 : 2);
+        if (mode != 2) d = c;
+        const unsigned xo = (unsigned)ds.x_off;
+#pragma unroll 1
+        for (int j = wj; j < ds.J; j += jq) {
+          const int q0 = j * PMDI_FB;
+          const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+          const int fo = q0 + 2 * lane;
+          double vs = 0.0, v;
+          if (ds.type == T_GAUSSIAN) {
+            const long long so = (long long)c * ds.Dp + fo;
+            v = gauss_block(ds.sum + so, ds.beta + so, ds.mu + so, ds.lamn + so, (long long)(d - c) * ds.Dp,
+                            ds.aux + (long long)c * ds.J + j, ds.aux + (long long)d * ds.J + j, ds.flag + fo, nit,
+                            mode, nc, xp + xo + fo * 8u, xc + xo + fo * 8u, &vs);
+          } else if (ds.type == T_NEGBINOM) {
+            v = nb_block(ds.S + (long long)c * ds.Dp + fo, (long long)(d - c) * ds.Dp, ds.aux + (long long)c * ds.J + j,
+                         ds.aux + (long long)d * ds.J + j, nit, mode, nc, xp + xo + fo * 4u, xc + xo + fo * 4u,
+                         (unsigned)__cvta_generic_to_shared(T.lf), sp.lf_T, &vs);
+          } else {
+            v = cat_block(pd.cw + ((long long)c * ds.Dp + fo) * pd.wpf, (long long)(d - c) * ds.Dp * pd.wpf, pd.wpf,
+                          pd.fpw, nit, mode, xp + xo + fo * 4u, xc + xo + fo * 4u, &vs);
+          }
+          if (lane == 0) {
+            const int ri = ds.J <= jq ? sub * jq + j : j;  // rows wider than 16 blocks: one row at a time
+            sm.red[buf][0][ri] = v;
+            sm.red[buf][1][ri] = vs;
+          }
+        }
       }
-      __syncwarp();
-      obs_ok = st;
     }
-    int k = 0;
+    __syncthreads();
+    if (active && wj == 0 && lane == 0) {  // the row's blocks in order, the size constant first
+      const DsDev& ds = sp.ds[k];
+      const int r0 = ds.J <= jq ? sub * jq : 0;
+      double v = __ldg(ds.rc + nc + (mode ? 1 : 0));
 #pragma unroll 1
-    while (k + 1 < K && idx >= sm.ibase[b][k + 1]) ++k;
-    const DsDev& ds = sp.ds[k];
-    const PoolDev& pd = sp.pd[k];
-    const int qb = sm.qb[b][k], JQ = (ds.J + qb - 1) / qb;
-    const int rel = idx - sm.ibase[b][k];
-    const int li = rel / JQ, q = rel - li * JQ;
-    const int j0 = q * qb, j1 = min(ds.J, j0 + qb);
-    const int c = ldcg_i32(pd.live + li);
-    const int tot = pp >= 0 ? ldcg_i32(pd.chosen + (size_t)pp * pd.cap + c) : 0;
-    const int nc = ldcg_i32(ds.n + c);
-    if (tot == 0) {
-      double v = pool_eval_plain(sp, k, c, j0, j1, nc, xc, T.lf, lane);
-      if (lane == 0) {
-        if (q == 0) { v = __ldg(ds.rc + nc) + v; atomicAdd(&sm.rows_eval[k], 1u); }  // rc first: the order of the sum
-        __stcg(ds.part + (long long)c * ds.J + j0, v);
-        for (int j = j0 + 1; j < j1; ++j) __stcg(ds.part + (long long)c * ds.J + j, 0.0);
+      for (int j = 0; j < ds.J; ++j) v += sm.red[buf][0][r0 + j];
+      __stcg(sp.pd[k].lp + d, v);
+      if (mode == 2) {
+        double vs = __ldg(ds.rc + nc);
+#pragma unroll 1
+        for (int j = 0; j < ds.J; ++j) vs += sm.red[buf][1][r0 + j];
+        __stcg(sp.pd[k].lp + c, vs);
       }
-    } else if (tot == ldcg_i32(pd.refcnt + c)) {  // every reference chose it: in place (src/pmdi.jl:284-286)
-      double dummy;
-      double v = pool_eval_cow<false>(sp, k, c, c, j0, j1, nc + 1, xp, xc, T.lf, lane, &dummy);
-      if (lane == 0) {
-        if (q == 0) { v = __ldg(ds.rc + nc + 1) + v; atomicAdd(&sm.rows_eval[k], 1u); }
-        __stcg(ds.part + (long long)c * ds.J + j0, v);
-        for (int j = j0 + 1; j < j1; ++j) __stcg(ds.part + (long long)c * ds.J + j, 0.0);
-      }
-    } else {  // split: the choosers' copy goes to row d, the others keep c (src/pmdi.jl:288-309)
-      const int d = ldcg_i32(pd.dst + (size_t)pp * pd.cap + c);
-      double vs;
-      double vd = pool_eval_cow<true>(sp, k, c, d, j0, j1, nc + 1, xp, xc, T.lf, lane, &vs);
-      if (lane == 0) {
-        if (q == 0) {
-          vs = __ldg(ds.rc + nc) + vs;
-          vd = __ldg(ds.rc + nc + 1) + vd;
-          atomicAdd(&sm.rows_eval[k], 2u);
-        }
-        __stcg(ds.part + (long long)c * ds.J + j0, vs);
-        __stcg(ds.part + (long long)d * ds.J + j0, vd);
-        for (int j = j0 + 1; j < j1; ++j) {
-          __stcg(ds.part + (long long)c * ds.J + j, 0.0);
-          __stcg(ds.part + (long long)d * ds.J + j, 0.0);
-        }
-      }
+      atomicAdd(&sm.rows_eval[k], mode == 2 ? 2u : 1u);
     }
   }
 }
 
 // Deferred bookkeeping of the rows this CTA's leaders resolved at the previous step: after the
-// barrier that follows R, nobody reads the old counts any more.  Thread per unit.
+// barrier that follows R, nobody reads the old counts any more.  Thread per unit, from the last
+// warp downwards (the first warps propose).
 __device__ __forceinline__ void pool_duties(const SweepParams& sp, const PoolTables& T, int nu, int pp) {
-  for (int u = threadIdx.x; u < nu; u += PMDI_NT) {
+#pragma unroll 1
+  for (int u = PMDI_NT - 1 - (int)threadIdx.x; u < nu; u += PMDI_NT) {
     const int duty = T.u_duty[u];
     if (!duty) continue;
-    const int k = u % sp.K;
+    const int k = T.u_ks[u] & 0xff;
     const PoolDev& pd = sp.pd[k];
     const int c = T.u_dc[u], d = T.u_dd[u], tot = T.u_dtot[u];
     __stcg(pd.chosen + (size_t)pp * pd.cap + c, 0);
@@ -309,9 +305,11 @@ __device__ __forceinline__ void pool_duties(const SweepParams& sp, const PoolTab
 // R phase for this CTA's units: the row each chooser's label maps to from now on.  Thread per unit.
 __device__ __forceinline__ void pool_resolve_units(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int nu,
                                                    int par) {
-  const int K = sp.K, N = sp.N, G = sp.G;
+  const int N = sp.N, G = sp.G;
+#pragma unroll 1
   for (int u = threadIdx.x; u < nu; u += PMDI_NT) {
-    const int k = u % K, slot = (int)blockIdx.x + (u / K) * G;
+    const int ks = T.u_ks[u];
+    const int k = ks & 0xff, slot = (int)blockIdx.x + (ks >> 8) * G;
     const PoolDev& pd = sp.pd[k];
     const int c = T.u_c[u];
     const int tot = ldcg_i32(pd.chosen + (size_t)par * pd.cap + c);
@@ -335,7 +333,7 @@ __device__ __forceinline__ void pool_resolve_units(const SweepParams& sp, PoolSm
 }
 
 // this CTA's (max, sum w, sum w^2) over its particles' log-weights; one warp
-__device__ __forceinline__ void pool_cta_partial(const SweepParams& sp, const PoolTables& T, int ns, int par) {
+__device__ __noinline__ void pool_cta_partial(const SweepParams& sp, const PoolTables& T, int ns, int par) {
   const int lane = threadIdx.x & 31;
   double m = -INFINITY;
 #pragma unroll 1
@@ -357,72 +355,109 @@ __device__ __forceinline__ void pool_cta_partial(const SweepParams& sp, const Po
 }
 
 // Combine `cnt` partials (max, s1, s2, stride `str` doubles) in a fixed order; one warp; every lane
-// returns the same bits.
-__device__ __forceinline__ void pool_combine(const double* ep, int cnt, int str, double& mx, double& num, double& den) {
+// returns the same bits.  Loads go out eight per lane at a time (one L2 round trip per 256 partials).
+__device__ __noinline__ void pool_combine(const double* ep, int cnt, int str, double& mx, double& num, double& den) {
   const int lane = threadIdx.x & 31;
   mx = -INFINITY;
 #pragma unroll 1
-  for (int c = lane; c < cnt; c += 32) mx = fmax(mx, ldcg_f64(ep + (size_t)str * c));
+  for (int c0 = 0; c0 < cnt; c0 += 256) {
+    double v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + lane + 32 * i;
+      v[i] = c < cnt ? ldcg_f64(ep + (size_t)str * c) : -INFINITY;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mx = fmax(mx, v[i]);
+  }
   mx = warp_max(mx);
   num = 0.0; den = 0.0;
 #pragma unroll 1
-  for (int c = lane; c < cnt; c += 32) {
-    const double e = pm_exp(ldcg_f64(ep + (size_t)str * c) - mx);
-    num += ldcg_f64(ep + (size_t)str * c + 1) * e;
-    den += ldcg_f64(ep + (size_t)str * c + 2) * (e * e);
+  for (int c0 = 0; c0 < cnt; c0 += 256) {
+    double m[8], a[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = c0 + lane + 32 * i;
+      if (c < cnt) {
+        m[i] = ldcg_f64(ep + (size_t)str * c);
+        a[i] = ldcg_f64(ep + (size_t)str * c + 1);
+        b[i] = ldcg_f64(ep + (size_t)str * c + 2);
+      } else { m[i] = -INFINITY; a[i] = 0.0; b[i] = 0.0; }
+    }
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) {
+      if (c0 + lane + 32 * i < cnt) {
+        const double e = pm_exp(m[i] - mx);
+        num += a[i] * e;
+        den += b[i] * (e * e);
+      }
+    }
   }
   num = warp_sum(num);
   den = warp_sum(den);
 }
 
 // Proposal of one unit (dataset k of a particle slot) at step `step`, one warp: src/pmdi.jl:223-265.
+template <bool DBG>
 __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int u, int step,
                                           int ns) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = sp.K, N = sp.N, P = sp.P, par = step & 1;
-  const int Npad = (N + 31) & ~31;
-  const int k = u % K, sl = u / K, slot = (int)blockIdx.x + sl * sp.G;
-  const DsDev& ds = sp.ds[k];
+  const int ks = T.u_ks[u];
+  const int k = ks & 0xff, sl = ks >> 8;
   const PoolDev& pd = sp.pd[k];
-  const int p = sp.slot0 + slot;  // logical particle
-  double* lps = T.lp_s + (size_t)warp * Npad;
-  const int* rm = T.rm_s + (size_t)u * N;
-  const int J = ds.J;
-  double uu = 0.0;
-  if (p != 0) uu = sp.tape_alloc ? __ldg(sp.tape_alloc + ((size_t)step * K + k) * P + p)
-                                 : pm_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
+  const int p = sp.slot0 + (int)blockIdx.x + sl * sp.G;  // logical particle
+  double* lps = T.lp_s + warp * ((N + 31) & ~31);
+  const int* rm = T.rm_s + u * N;
+  const int empty = pd.cap - 1;
+  TRACE(step, 42)
+  // lp of the unit's N labels: one number per row (E phase); two labels per lane go out together
   double mx = -INFINITY;
   int occ = 0;
 #pragma unroll 1
-  for (int m0 = 0; m0 < N; m0 += 32) {
-    const int m = m0 + lane;
-    double a = -INFINITY;
-    bool o = false;
-    if (m < N) {
-      const int r = rm[m];
-      o = r != pd.cap - 1;
-      const double* pr = ds.part + (long long)r * J;
-      a = ldcg_f64(pr);  // rc[n] + the first block range (E phase), then the other ranges in order;
-#pragma unroll 1           // slots inside a range hold 0.0 (x + 0.0 == x): the layout needs no item size
-      for (int j = 1; j < J; ++j) a += ldcg_f64(pr + j);
-      lps[m] = a;
-      if (sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + m] = a;
+  for (int m0 = 0; m0 < N; m0 += 64) {
+    const int ma = m0 + lane, mb = ma + 32;
+    const int ra = ma < N ? rm[ma] : empty, rb = mb < N ? rm[mb] : empty;
+    const double a = ldcg_f64(pd.lp + ra), b = ldcg_f64(pd.lp + rb);
+    if (ma < N) {
+      lps[ma] = a;
+      mx = fmax(mx, a);
+      if (DBG && sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + ma] = a;
     }
-    occ += __popc(__ballot_sync(FULL, o));
-    mx = fmax(mx, a);
+    if (mb < N) {
+      lps[mb] = b;
+      mx = fmax(mx, b);
+      if (DBG && sp.dbg_lp) sp.dbg_lp[(((size_t)step * K + k) * P + p) * N + mb] = b;
+    }
+    occ += __popc(__ballot_sync(FULL, ra != empty)) + __popc(__ballot_sync(FULL, rb != empty));
   }
+  double uu = 0.0;
+  if (p != 0) uu = sp.tape_alloc ? __ldg(sp.tape_alloc + ((size_t)step * K + k) * P + p)
+                                 : pm_uniform(sp.seed, sp.iter, DRAW_ALLOC, step, k, p);
   mx = warp_max(mx);
   __syncwarp();
+  TRACE(step, 43)
   // f = exp(lp - max) * Pi ; sequential cumsum over labels (src/pmdi.jl:236-241)
 #pragma unroll 1
   for (int m = lane; m < N; m += 32) lps[m] = pm_exp(lps[m] - mx) * T.Pi_s[k * N + m];
   __syncwarp();
+  TRACE(step, 44)
   if (lane == 0) {
     double run = 0.0;
+    int m = 0;
 #pragma unroll 1
-    for (int m = 0; m < N; ++m) { run += lps[m]; lps[m] = run; }
+    for (; m + 4 <= N; m += 4) {  // loads ahead of the dependent adds
+      const double v0 = lps[m], v1 = lps[m + 1], v2 = lps[m + 2], v3 = lps[m + 3];
+      run += v0; lps[m] = run;
+      run += v1; lps[m + 1] = run;
+      run += v2; lps[m + 2] = run;
+      run += v3; lps[m + 3] = run;
+    }
+#pragma unroll 1
+    for (; m < N; ++m) { run += lps[m]; lps[m] = run; }
   }
   __syncwarp();
+  TRACE(step, 45)
   const double tot = lps[N - 1];
   int label;
   if (p == 0) {
@@ -433,22 +468,24 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
     for (int m0 = 0; m0 < N - 1; m0 += 32) {
       const int m = m0 + lane;
       const bool hit = (m < N - 1) && (pm_div(lps[m < N ? m : 0], tot) > uu);  // strict '>' (:255)
-      const unsigned b = __ballot_sync(FULL, hit);
-      if (b) { label = m0 + __ffs(b) - 1; break; }
+      const unsigned bb = __ballot_sync(FULL, hit);
+      if (bb) { label = m0 + __ffs(bb) - 1; break; }
     }
   }
+  TRACE(step, 46)
   int rank = 1;
   const int c = rm[label];
   if (lane == 0) rank = atomicAdd(pd.chosen + (size_t)par * pd.cap + c, 1);  // in flight during the log below
   const double inc = pm_log(tot) + mx;
   int last_particle = 0;
+  TRACE(step, 47)
   if (lane == 0) {
     if (rank == 0) __stcg(pd.dst + (size_t)par * pd.cap + c, T.u_spare[u]);  // first chooser: the row a split would use
     T.u_c[u] = c; T.u_lab[u] = label; T.u_lead[u] = rank == 0;
 #pragma unroll 1
     for (int r = 0; r < sp.R; ++r)  // every rank back-traces the selected particle's lineage itself
       *on_rank(sp, sp.alloc_log + ((size_t)step * K + k) * P + p, r) = (uint8_t)label;
-    if (sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
+    if (DBG && sp.dbg_alloc) sp.dbg_alloc[((size_t)step * K + k) * P + p] = label + 1;
     atomicAdd(&sm.rows_ref[k], (unsigned)occ);
     // ---- weight increment; the K-th proposal of the particle folds its log-weight
     T.inc_s[sl * K + k] = inc;
@@ -472,7 +509,7 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
         }
       T.lw_s[sl] = w;
       __stcg(sp.lw + p, w);
-      if (sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
+      if (DBG && sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
       __threadfence_block();
       last_particle = (atomicAdd(&sm.pdone, 1) == ns - 1) ? 1 : 0;
     }
@@ -483,6 +520,7 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
     __threadfence_block();
     pool_cta_partial(sp, T, ns, par);
   }
+  TRACE(step, 48)
 }
 
 // draw_partstar (src/misc.jl:27-47) by CTA 0, all threads: anc_log[ev][P] (1-based, non-decreasing,
@@ -491,6 +529,7 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
 // moves to position 1; that index is traced through the swaps without moving anything.
 __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step, int ev, double mx, int* s_tmp) {
   const int P = sp.P, t = threadIdx.x;
+#pragma unroll 1
   for (int p = t; p < P; p += PMDI_NT) {
     sp.sc_w[p] = pm_exp(__ldcg(on_rank(sp, sp.lw + p, p / sp.Ps)) - mx);  // the holder's copy (NVLink when remote)
     const double us = sp.tape_shuffle ? sp.tape_shuffle[(size_t)step * P + p]
@@ -502,22 +541,27 @@ __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step,
   __syncthreads();
   if (t == 0) {  // pprob = cumsum(exp.(logweight .- max)), sequential (misc.jl:29)
     double acc = 0.0;
+#pragma unroll 1
     for (int p = 0; p < P; ++p) { acc += sp.sc_w[p]; sp.sc_pp[p] = acc; }
   } else if (t == 32) {  // u, u + 1/P, ... by repeated addition (misc.jl:28,35)
     const double r = sp.tape_resamp ? sp.tape_resamp[step] : pm_uniform(sp.seed, sp.iter, DRAW_RESAMP, step, 0, 0);
     double u = r / (double)P;
+#pragma unroll 1
     for (int i = 0; i < P; ++i) { sp.sc_u[i] = u; u += 1.0 / (double)P; }
   } else if (t == 64) {  // index of the pre-shuffle element that ends at position 1
     int tt = 0;
+#pragma unroll 1
     for (int pos = 2; pos <= P; ++pos)
       if (sp.sc_j[pos - 1] - 1 == tt) tt = pos - 1;
     s_tmp[0] = tt;
   }
   __syncthreads();
   const double tot = sp.sc_pp[P - 1];
+#pragma unroll 1
   for (int i = t; i < P; i += PMDI_NT) {  // first p with pprob[p]/last >= u_i (misc.jl:33-38)
     const double ui = sp.sc_u[i];
     int lo = 0, hi = P;
+#pragma unroll 1
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
       if (pm_div(sp.sc_pp[mid], tot) >= ui) hi = mid; else lo = mid + 1;
@@ -527,6 +571,7 @@ __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step,
   __syncthreads();
   const int drop = s_tmp[0];
   int* anc = sp.anc_log + (size_t)ev * P;
+#pragma unroll 1
   for (int i = t; i < P; i += PMDI_NT) {
     const int a = (i == 0) ? 1 : ((i - 1 < drop) ? sp.sc_anc0[i - 1] : sp.sc_anc0[i]);
     anc[i] = a;
@@ -535,6 +580,7 @@ __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step,
   __syncthreads();
   if (t == 0) {
     int dup = 0;
+#pragma unroll 1
     for (int i = 1; i < P; ++i) dup += anc[i] == anc[i - 1];
     sp.ev_of_step[step] = ev;
     sp.counters[0] += 1;
@@ -545,11 +591,13 @@ __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step,
 // (re)load the owned units' row maps into shared memory and reserve one row per unit.  All threads.
 __device__ __noinline__ void pool_load_units(const SweepParams& sp, PoolSmem& sm, const PoolTables& T, int ns) {
   const int K = sp.K, N = sp.N, nu = ns * K;
+#pragma unroll 1
   for (int i = threadIdx.x; i < nu * N; i += PMDI_NT) {
     const int u = i / N, m = i - u * N;
     const int k = u % K, slot = (int)blockIdx.x + (u / K) * sp.G;
     T.rm_s[i] = ldcg_i32(sp.pd[k].rowmap + ((size_t)(sm.ev & 1) * sp.Ps + slot) * N + m);
   }
+#pragma unroll 1
   for (int u = threadIdx.x; u < nu; u += PMDI_NT) {
     const PoolDev& pd = sp.pd[u % K];
     const int fi = atomicSub(pd.ctr + 1, 1) - 1;
@@ -559,12 +607,13 @@ __device__ __noinline__ void pool_load_units(const SweepParams& sp, PoolSmem& sm
 }
 
 // One warp copies pool row `src` of the rank whose arena is `sdelta` bytes away into local row `dst`:
-// statistics, aux, the row's current predictive partials, the cluster size.
+// statistics, aux, the row's current predictive, the cluster size.
 __device__ __noinline__ void pool_row_pull(const SweepParams& sp, int k, long long sdelta, long long src, long long dst) {
   const DsDev& ds = sp.ds[k];
   const int lane = threadIdx.x & 31, Dp = ds.Dp;
 #define PMDI_SRC(ptr_) ((decltype(ptr_))((const char*)(ptr_) + sdelta))
   if (ds.type == T_GAUSSIAN) {
+#pragma unroll 1
     for (int q = 2 * lane; q < Dp; q += 64) {
       const double2 a = ldcg_f64x2(PMDI_SRC(ds.mu) + src * Dp + q), b = ldcg_f64x2(PMDI_SRC(ds.lamn) + src * Dp + q);
       const double2 c = ldcg_f64x2(PMDI_SRC(ds.sum) + src * Dp + q), d = ldcg_f64x2(PMDI_SRC(ds.beta) + src * Dp + q);
@@ -574,17 +623,20 @@ __device__ __noinline__ void pool_row_pull(const SweepParams& sp, int k, long lo
   } else if (ds.type == T_CATEGORICAL) {
     const PoolDev& pd = sp.pd[k];
     const long long W = (long long)Dp * pd.wpf;
+#pragma unroll 1
     for (long long q = 2 * lane; q < W; q += 64)
       *(ulonglong2*)(pd.cw + dst * W + q) = ldcg_u64x2(PMDI_SRC(pd.cw) + src * W + q);
   } else {
+#pragma unroll 1
     for (int q = 2 * lane; q < Dp; q += 64)
       *(longlong2*)(ds.S + dst * Dp + q) = ldcg_i64x2(PMDI_SRC(ds.S) + src * Dp + q);
   }
-  for (int jj = lane; jj < ds.J; jj += 32) {
-    ds.aux[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + jj);
-    ds.part[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.part) + src * ds.J + jj);
+#pragma unroll 1
+  for (int jj = lane; jj < ds.J; jj += 32) ds.aux[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + jj);
+  if (lane == 0) {
+    ds.n[dst] = ldcg_i32(PMDI_SRC(ds.n) + src);
+    sp.pd[k].lp[dst] = ldcg_f64(PMDI_SRC(sp.pd[k].lp) + src);
   }
-  if (lane == 0) ds.n[dst] = ldcg_i32(PMDI_SRC(ds.n) + src);
 #undef PMDI_SRC
 }
 
@@ -604,6 +656,7 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
   const int* anc = sp.anc_log + (size_t)ev * sp.P;
   if (gt == 0 && st + 1 < sp.steps) {  // rows the E phase evaluated ahead of this decision (live now, dead after it)
     long long u = 0;
+#pragma unroll 1
     for (int k = 0; k < K; ++k) u += ldcg_i32(sp.pd[k].ctr);
     sp.counters[4] += u;
   }
@@ -613,6 +666,7 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
     const PoolDev& pd = sp.pd[k];
     const int* rm_old = pd.rowmap + (size_t)(ev & 1) * Ps * N;
     int* rm_new = pd.rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+#pragma unroll 1
     for (long long i = gt; i < (long long)Ps * N; i += GT) {
       const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
       const int a = ldcg_i32(anc + sp.slot0 + slot) - 1;
@@ -634,14 +688,17 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
         __stcg(rm_new + i, d);
       }
     }
+#pragma unroll 1
     for (long long r = gt; r < pd.cap; r += GT) __stcg(pd.refcnt + r, 0);
   }
+#pragma unroll 1
   for (int sl = threadIdx.x; sl < ns; sl += PMDI_NT) T.lw_s[sl] = 1.0;  // logweight .= 1.0 (src/pmdi.jl:319)
   if (!pool_gsync(sp, sm)) return false;
   // ---- A2: pull the reserved rows; the other children of a remote ancestor share its first child's map
   if (sp.R > 1) {
     const long long njobs = __ldcg(&sp.counters[5]);
     const long long gw = gt >> 5, GWp = GT >> 5;
+#pragma unroll 1
     for (long long job = gw; job < njobs; job += GWp) {
       const int4 jb = __ldcg(sp.pull_jobs + job);
       pool_row_pull(sp, jb.x, sp.peer_delta[jb.y], jb.z, jb.w);
@@ -650,29 +707,34 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
       int* rm_new = sp.pd[k].rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+#pragma unroll 1
       for (long long i = gt; i < (long long)Ps * N; i += GT) {
         const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
         const int a1 = ldcg_i32(anc + sp.slot0 + slot);
         if ((a1 - 1) / Ps == sp.rank) continue;
         int f = slot;
+#pragma unroll 1
         while (f > 0 && ldcg_i32(anc + sp.slot0 + f - 1) == a1) --f;
         if (f != slot) __stcg(rm_new + i, ldcg_i32(rm_new + (size_t)f * N + m));
       }
     }
   }
   if (gt == 0)
+#pragma unroll 1
     for (int k = 0; k < K; ++k) { __stcg(sp.pd[k].ctr, 1); __stcg(sp.pd[k].ctr + 1, 0); }  // the lists are rebuilt below
   if (!pool_gsync(sp, sm)) return false;
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
     const PoolDev& pd = sp.pd[k];
     const int* rm_new = pd.rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+#pragma unroll 1
     for (long long i = gt; i < (long long)Ps * N; i += GT) atomicAdd(pd.refcnt + ldcg_i32(rm_new + i), 1);
   }
   if (!pool_gsync(sp, sm)) return false;
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
     const PoolDev& pd = sp.pd[k];
+#pragma unroll 1
     for (long long r = gt; r < pd.cap - 1; r += GT) {
       if (ldcg_i32(pd.refcnt + r) > 0) pd.live[atomicAdd(pd.ctr, 1)] = (int)r;
       else pd.freelist[atomicAdd(pd.ctr + 1, 1)] = (int)r;
@@ -684,6 +746,7 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
   if (!pool_xsync(sp, sm)) return false;
   if (gt == 0 && st + 1 < sp.steps) {
     long long u = 0;
+#pragma unroll 1
     for (int k = 0; k < K; ++k) u += ldcg_i32(sp.pd[k].ctr);
     sp.counters[4] -= u;
   }
@@ -724,6 +787,7 @@ __device__ __noinline__ void pool_resolve_ranks(const SweepParams& sp, PoolSmem&
     const unsigned long long* f = (const unsigned long long*)(base + (size_t)lane * 4 + 3);
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
+#pragma unroll 1
     while (ld_acquire_sys_u64(f) < (unsigned long long)(t + 1)) {
       if (((++spins) & 0x3ffu) == 0) {
         if (__ldcg(sp.err) != 0) break;
@@ -742,13 +806,10 @@ __device__ __noinline__ void pool_resolve_ranks(const SweepParams& sp, PoolSmem&
   }
 }
 
-extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __grid_constant__ SweepParams sp) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ __align__(16) PoolSmem sm;
-  __shared__ int s_tmp[4];
-
+template <bool DBG>
+__device__ __forceinline__ void pool_sweep_body(const SweepParams& sp, PoolSmem& sm, unsigned char* smem_raw, int* s_tmp) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int NW = PMDI_NT / 32;
+  const int NW = POOL_NW;
   const int cta = blockIdx.x;
   const int K = sp.K, N = sp.N, steps = sp.steps, G = sp.G;
   const int Npad = (N + 31) & ~31;
@@ -774,44 +835,53 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
   T.u_dd = T.u_dc + MU;
   T.u_dtot = T.u_dd + MU;
   T.u_spare = T.u_dtot + MU;
-  T.rm_s = T.u_spare + MU;
+  T.u_ks = T.u_spare + MU;
+  T.rm_s = T.u_ks + MU;
+#pragma unroll 1
   for (int i = tid; i < sp.lf_T; i += PMDI_NT) T.lf[i] = sp.lf_glob[i];
+#pragma unroll 1
   for (int i = tid; i < K * N; i += PMDI_NT) T.Pi_s[i] = sp.Pi[i];
+#pragma unroll 1
   for (int sl = tid; sl < ns; sl += PMDI_NT) { T.lw_s[sl] = sp.lw_init; T.pcount[sl] = 0; }
-  for (int u = tid; u < nu; u += PMDI_NT) T.u_duty[u] = 0;
+#pragma unroll 1
+  for (int u = tid; u < nu; u += PMDI_NT) { T.u_duty[u] = 0; T.u_ks[u] = (u % K) | ((u / K) << 8); }
   if (tid < PMDI_MAX_K) { sm.rows_eval[tid] = 0; sm.rows_ref[tid] = 0; }
   if (tid < 8) sm.tacc[tid] = 0;
+  if (tid < POOL_NW) sm.tr_n[tid] = 0;
   if (tid == 0) {
-    sm.res_flag = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.epoch = 0; sm.xepoch = 0; sm.res_mx = 0.0;
+    sm.res_flag = 0; sm.res_next = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.epoch = 0; sm.xepoch = 0; sm.res_mx = 0.0;
+#pragma unroll 1
     for (int b = 0; b < sp.obs_ring; ++b) mbar_init(&sm.obs_bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    pool_snapshot(sp, sm, 0);
   }
+  if (warp == NW - 1) pool_snapshot(sp, sm, 0);
   __syncthreads();
   if (tid == 0)
+#pragma unroll 1
     for (int s = 0; s < sp.obs_ring; ++s) pool_issue_obs(sp, s, xring, sm.obs_bar);
   pool_load_units(sp, sm, T, ns);
 
-  const bool timing = sp.phase_ns != nullptr;
+  const bool timing = DBG && sp.phase_ns != nullptr;
   unsigned long long tw_prev = timing ? globaltimer_ns() : 0ull;
 #define PHASE_MARK(i_)                                                 \
-  if (timing && lane == 0) {                                           \
+  if (DBG && timing && lane == 0) {                                    \
     const unsigned long long now_ = globaltimer_ns();                  \
     atomicAdd(&sm.tacc[i_], now_ - tw_prev);                           \
     tw_prev = now_;                                                    \
   }
 
   int obs_ok = -1;
-  pool_eval_phase(sp, sm, T, 0, -1, xring, obs_ok);
+  pool_eval_rows(sp, sm, T, 0, -1, xring, obs_ok);
   PHASE_MARK(1)
-  if (!pool_gsync(sp, sm)) return;  // B1(0)
+  if (!pool_gsync(sp, sm, sp.R == 1)) return;  // B1(0)
   PHASE_MARK(0)
 #pragma unroll 1
   for (int t = 0; t < steps; ++t) {
     const int par = t & 1;
-    // ---- P(t)
+    TRACE(t, 40)
+    // ---- P(t): the last warp keeps house, the others propose
     if (t > 0) {
-      if (tid == 0) pool_issue_obs(sp, t - 1 + sp.obs_ring, xring, sm.obs_bar);  // x[t-1] is dead: its slot refills
+      if (tid == PMDI_NT - 1) pool_issue_obs(sp, t - 1 + sp.obs_ring, xring, sm.obs_bar);  // x[t-1] is dead: its slot refills
       pool_duties(sp, T, nu, par ^ 1);
       if (sp.R > 1) {  // the ranks' partials of step t-1 have had E(t) to arrive
         if (warp == NW - 1) pool_resolve_ranks(sp, sm, t - 1);
@@ -822,31 +892,39 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
         PHASE_MARK(6)
       }
     }
-    if (tid == 0 && t + 1 < steps) pool_snapshot(sp, sm, par ^ 1);  // item list of E(t+1): the rows live now
+    if (warp == NW - 1 && t + 1 < steps) pool_snapshot(sp, sm, par ^ 1);  // row tasks of E(t+1): the rows live now
+    TRACE(t, 41)
 #pragma unroll 1
-    for (int u = warp; u < nu; u += NW) pool_propose(sp, sm, T, u, t, ns);
+    for (int u = warp; u < nu; u += NW) pool_propose<DBG>(sp, sm, T, u, t, ns);
     PHASE_MARK(2)
+    TRACE(t, 49)
     if (!pool_gsync(sp, sm)) return;  // B2(t): every choice, reservation and ESS partial is in
-    PHASE_MARK(0)
+    PHASE_MARK(4)
+    TRACE(t, 50)
     // ---- R(t)
     pool_resolve_units(sp, sm, T, nu, par);
-    if (sp.R > 1) {
-      if (cta == 0 && warp == NW - 1) pool_push_rank_partial(sp, t);
-    } else if (warp == NW - 1) {  // calc_ESS (src/misc.jl:15-25), same bits in every CTA; the last warp has the fewest items
-      double mxv, num, den;
-      pool_combine(sp.ess_part + (size_t)par * G * 3, G, 3, mxv, num, den);
-      if (lane == 0) {
-        const bool res = (num * num) / den <= 0.5 * (double)sp.P;  // src/pmdi.jl:317
-        sm.res_mx = mxv;
-        sm.res_flag = res ? 1 : 0;
-        if (!res && cta == 0) sp.ev_of_step[t] = -1;
+    TRACE(t, 51)
+    if (cta == 0 && warp == NW - 1) {
+      if (sp.R > 1) {
+        pool_push_rank_partial(sp, t);
+      } else {  // calc_ESS (src/misc.jl:15-25); the decision travels with CTA 0's arrival at B1(t+1)
+        double mxv, num, den;
+        pool_combine(sp.ess_part + (size_t)par * G * 3, G, 3, mxv, num, den);
+        if (lane == 0) {
+          const bool res = (num * num) / den <= 0.5 * (double)sp.P;  // src/pmdi.jl:317
+          sm.res_mx = mxv;
+          sm.res_next = res ? 1 : 0;
+          if (!res) sp.ev_of_step[t] = -1;
+        }
       }
     }
     PHASE_MARK(3)
+    TRACE(t, 52)
     // ---- E(t+1)
-    if (t + 1 < steps) pool_eval_phase(sp, sm, T, t + 1, par, xring, obs_ok);
+    if (t + 1 < steps) pool_eval_rows(sp, sm, T, t + 1, par, xring, obs_ok);
     PHASE_MARK(1)
-    if (!pool_gsync(sp, sm)) return;  // B1(t+1)
+    TRACE(t, 56)
+    if (!pool_gsync(sp, sm, sp.R == 1)) return;  // B1(t+1)
     PHASE_MARK(0)
   }
   // ---- after the last observation: its bookkeeping (cluster sizes), and its ESS test
@@ -860,6 +938,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
     atomicAdd(sp.rows_ref + tid, (unsigned long long)sm.rows_ref[tid]);
   }
   if (cta == 0)  // after a final resampling all log-weights are 1.0 (src/pmdi.jl:319)
+#pragma unroll 1
     for (int p = tid; p < sp.P; p += PMDI_NT)
       sp.lw_out[p] = final_res ? 1.0 : __ldcg(on_rank(sp, sp.lw + p, p / sp.Ps));
   if (timing && tid < 8) sp.phase_ns[(size_t)cta * 8 + tid] = sm.tacc[tid] / NW;
@@ -869,6 +948,34 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
 #undef PHASE_MARK
 }
 
+// The parameter block lives in shared memory for the whole sweep: the helpers take it by reference, and a
+// reference to the kernel's parameter space turns every field access into a generic load from the
+// constant window.
+#define POOL_KERNEL_PROLOGUE                                                                              \
+  extern __shared__ __align__(16) unsigned char smem_raw[];                                               \
+  __shared__ __align__(16) PoolSmem sm;                                                                   \
+  __shared__ int s_tmp[4];                                                                                \
+  __shared__ __align__(16) SweepParams sp_s;                                                              \
+  {                                                                                                       \
+    static_assert(sizeof(SweepParams) % 16 == 0, "SweepParams is copied in 16-byte words");              \
+    const int4* src = (const int4*)&sp_in;                                                                \
+    int4* dst = (int4*)&sp_s;                                                                             \
+    _Pragma("unroll 1") for (int i = threadIdx.x; i < (int)(sizeof(SweepParams) / 16); i += PMDI_NT) dst[i] = src[i]; \
+  }                                                                                                       \
+  __syncthreads();
+
+// production kernel: no debug capture, no tracing, no phase timing in the instruction stream
+extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __grid_constant__ SweepParams sp_in) {
+  POOL_KERNEL_PROLOGUE
+  pool_sweep_body<false>(sp_s, sm, smem_raw, s_tmp);
+}
+// PMDI_SWEEP_DEBUG / PMDI_SWEEP_TIME_PHASES / PMDI_TRACE_STEP
+extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool_dbg(const __grid_constant__ SweepParams sp_in) {
+  POOL_KERNEL_PROLOGUE
+  pool_sweep_body<true>(sp_s, sm, smem_raw, s_tmp);
+}
+#undef TRACE
+
 // ------------------------------------------------------------------------------------------------
 // set-up and finish kernels of the pool engine
 // ------------------------------------------------------------------------------------------------
@@ -876,6 +983,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool(const __gr
 // all rows of a dataset's packed categorical counts to zero (the other statistics: k_init_rows)
 __global__ void k_pool_init_rows(PoolDev pd, long long words) {
   const long long stride = (long long)gridDim.x * blockDim.x;
+#pragma unroll 1
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) pd.cw[i] = 0ull;
 }
 
@@ -887,8 +995,11 @@ __global__ void k_pool_init(SweepParams sp) {
   const PoolDev pd = sp.pd[k];
   const DsDev& ds = sp.ds[k];
   __shared__ int s_nfree0;
+#pragma unroll 1
   for (int i = t; i < 2 * pd.cap; i += NT) { pd.chosen[i] = 0; pd.dst[i] = -1; }
+#pragma unroll 1
   for (int r = t; r < pd.cap; r += NT) pd.refcnt[r] = (r < N && ds.n[r] > 0) ? Ps : 0;
+#pragma unroll 1
   for (long long i = t; i < (long long)Ps * N; i += NT) {
     const int m = (int)(i % N);
     pd.rowmap[i] = ds.n[m] > 0 ? m : pd.cap - 1;
@@ -896,6 +1007,7 @@ __global__ void k_pool_init(SweepParams sp) {
   if (t == 0) {
     int nl = 0, nf = 0;
     pd.live[nl++] = pd.cap - 1;
+#pragma unroll 1
     for (int m = 0; m < N; ++m) {
       if (ds.n[m] > 0) pd.live[nl++] = m;
       else pd.freelist[nf++] = m;
@@ -906,6 +1018,7 @@ __global__ void k_pool_init(SweepParams sp) {
   }
   __syncthreads();
   const int nf0 = s_nfree0;
+#pragma unroll 1
   for (int r = N + t; r < pd.cap - 1; r += NT) pd.freelist[nf0 + (r - N)] = r;
   __syncthreads();
   if (t == 0) { pd.refcnt[pd.cap - 1] = POOL_BIG_REF; ds.n[pd.cap - 1] = 0; }
@@ -921,10 +1034,12 @@ __global__ void k_pool_prefix_cat(SweepParams sp, int k, const int* members, con
   const int b = off[k * (sp.N + 1) + m], e = off[k * (sp.N + 1) + m + 1];
   const int* mem = members + (size_t)k * (sp.n1 - 1) + b;
   unsigned long long* w = pd.cw + ((size_t)m * ds.Dp + q) * pd.wpf;
+#pragma unroll 1
   for (int i = 0; i < pd.wpf; ++i) w[i] = 0ull;
   if (ds.flag[q]) {
     const int* x = (const int*)ds.x;
     const int fw = 64 / pd.fpw;
+#pragma unroll 1
     for (int t = 0; t < e - b; ++t) {
       const int lv = x[(size_t)mem[t] * ds.Dp + q] - 1;
       w[lv / pd.fpw] += 1ull << ((lv % pd.fpw) * fw);
@@ -940,45 +1055,59 @@ __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long
   const int t = threadIdx.x, NT = blockDim.x, P = sp.P, K = sp.K, N = sp.N;
   __shared__ double red[32];
   double mx = -INFINITY;
+#pragma unroll 1
   for (int p = t; p < P; p += NT) mx = fmax(mx, sp.lw_out[p]);
   mx = warp_max(mx);
   if ((t & 31) == 0) red[t >> 5] = mx;
   __syncthreads();
   mx = red[0];
+#pragma unroll 1
   for (int i = 1; i < (NT >> 5); ++i) mx = fmax(mx, red[i]);
+#pragma unroll 1
   for (int p = t; p < P; p += NT) sp.sc_w[p] = exp(sp.lw_out[p] - mx);
   __syncthreads();
   if (t == 0) {
     double tot = 0.0;
+#pragma unroll 1
     for (int p = 0; p < P; ++p) tot += sp.sc_w[p];
     const double u = sp.tape_select ? sp.tape_select[0] : pmdi_philox_uniform(sp.seed, sp.iter, DRAW_SELECT, 0, 0, 0);
     const double thr = u * tot;
     int i = 0;
     double cw = sp.sc_w[0];
+#pragma unroll 1
     while (cw < thr && i < P - 1) { ++i; cw += sp.sc_w[i]; }
     *p_star_out = i + 1;
     int cur = i;  // lineage of p_star through the resampling events, backwards (src/__pmdi.jl:285)
+#pragma unroll 1
     for (int st = sp.steps - 1; st >= 0; --st) {
       const int ev = sp.ev_of_step[st];
       if (ev >= 0 && !compat) cur = sp.anc_log[(size_t)ev * P + cur] - 1;
       cur_at[st] = cur;
     }
   }
+#pragma unroll 1
   for (size_t i = t; i < (size_t)K * sp.n_obs; i += NT) s_out[i] = sp.s_in[i];
+#pragma unroll 1
   for (int i = t; i < N * K; i += NT) label_counts[i] = 0;
+#pragma unroll 1
   for (int i = t; i < K * (K - 1) / 2; i += NT) pair_agree[i] = 0;
   __syncthreads();
+#pragma unroll 1
   for (int idx = t; idx < sp.steps * K; idx += NT) {
     const int st = idx / K, k = idx - st * K;
     const int obs = sp.order[sp.n1 - 1 + st];
     s_out[(size_t)k * sp.n_obs + obs] = 1 + sp.alloc_log[((size_t)st * K + k) * P + cur_at[st]];
   }
   __syncthreads();
+#pragma unroll 1
   for (size_t i = t; i < (size_t)K * sp.n_obs; i += NT)
     atomicAdd((unsigned long long*)&label_counts[(i / sp.n_obs) * N + (s_out[i] - 1)], 1ull);
+#pragma unroll 1
   for (int i = t; i < sp.n_obs; i += NT) {
     int idx = 0;
+#pragma unroll 1
     for (int k1 = 0; k1 < K - 1; ++k1)
+#pragma unroll 1
       for (int k2 = k1 + 1; k2 < K; ++k2) {
         if (s_out[(size_t)k1 * sp.n_obs + i] == s_out[(size_t)k2 * sp.n_obs + i])
           atomicAdd((unsigned long long*)&pair_agree[idx], 1ull);
@@ -988,6 +1117,7 @@ __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long
   if (cluster_n && sp.engine == 0) {
     const int ev = (int)sp.counters[2];
     const int* slot = sp.slot_of + (ev & 1) * P;
+#pragma unroll 1
     for (size_t idx = t; idx < (size_t)K * P * N; idx += NT) {
       const int k = (int)(idx / ((size_t)P * N));
       const size_t rem = idx - (size_t)k * P * N;
@@ -998,6 +1128,7 @@ __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long
   }
   if (cluster_n && sp.engine == 1) {
     const int ev = (int)sp.counters[2];
+#pragma unroll 1
     for (size_t idx = t; idx < (size_t)K * P * N; idx += NT) {
       const int k = (int)(idx / ((size_t)P * N));
       const size_t rem = idx - (size_t)k * P * N;
