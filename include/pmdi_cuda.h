@@ -138,10 +138,14 @@ typedef struct pmdi_sweep_out {
                              both datasets, src/update_hypers.jl:109-115                        */
   int64_t  rows_referenced[8]; /* per dataset: occupied (particle, label) clusters the proposals read;
                              rows_evaluated counts each physical row once per observation       */
-  int32_t  engine;        /* 1 copy-on-write pool, 0 dense                                     */
+  int32_t  engine;        /* 2 copy-on-write pool, evaluations one observation ahead (one grid barrier per step);
+                             1 copy-on-write pool, two barriers per step; 0 dense                 */
   int64_t  rows_evaluated_ahead; /* pool engine: rows evaluated for observation t+1 before the resampling
                              decision of step t removed them (evaluation runs ahead of the ESS test);
                              rows_evaluated - rows_evaluated_ahead = the reference's calc_logprob calls */
+  int64_t  rows_computed[8]; /* per dataset: row evaluations the device performed.  Engine 2 evaluates every
+                             live row AND its child (the row plus the previous observation) one step ahead,
+                             so this is about twice rows_evaluated; engines 0/1: equal to rows_evaluated  */
 } pmdi_sweep_out;
 
 /*

@@ -246,8 +246,8 @@ __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
     if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, n, (const double*)xs_raw, lane);
     else if (ds.type == T_CATEGORICAL && sp.engine) {
       const PoolDev& pd = sp.pd[k];
-      const int base = j * PMDI_FB + 2 * lane;
-      const int nits = min(PMDI_FB / PMDI_WF, (ds.Dp - j * PMDI_FB) / PMDI_WF);
+      const int base = j * ds.FB + 2 * lane;
+      const int nits = min(ds.FB / PMDI_WF, (ds.Dp - j * ds.FB) / PMDI_WF);
       double unused;
       v = cat_block(pd.cw + ((size_t)row * ds.Dp + base) * pd.wpf, 0, pd.wpf, pd.fpw, nits, 0, 0u,
                     (unsigned)__cvta_generic_to_shared(xs_raw) + base * 4u, &unused);

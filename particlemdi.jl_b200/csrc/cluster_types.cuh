@@ -20,8 +20,8 @@
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double gauss_eval_block(const DsDev& ds, long long row, int j, int n,
                                                    const double* xs, int lane) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   const double* mu = ds.mu + row * ds.Dp + q0 + 2 * lane;
   const double* lm = ds.lamn + row * ds.Dp + q0 + 2 * lane;
   double2 m[4], l[4];
@@ -63,8 +63,8 @@ __device__ __forceinline__ double div_const(double x, double c, double rc) {
 // the flagged features) is taken as one log of the lane's product of <= 8 factors.
 __device__ __noinline__ void gauss_add_block(const DsDev& ds, long long row, int j, int n,
                                                 const double* xs, int lane) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   const double nn = (double)n;
   const double c1 = __dadd_rn(__dadd_rn(nn, -1.0), 0.001);      // n - 1 + kappa
   const double c2 = __dmul_rn(2.0, __dadd_rn(nn, 0.001));       // 2 (n + kappa)
@@ -185,8 +185,8 @@ __device__ __noinline__ double gauss_fused_raw(double* sum_p, double* beta_p, do
 }
 __device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long row, int j, int n,
                                                     const double* xp, const double* xc, int lane) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   const long long o = row * ds.Dp + q0 + 2 * lane;
   return gauss_fused_raw(ds.sum + o, ds.beta + o, ds.mu + o, ds.lamn + o, ds.aux + row * ds.J + j,
                          ds.flag + q0 + 2 * lane, nit, n, xp + q0 + 2 * lane, xc + q0 + 2 * lane, lane);
@@ -194,8 +194,8 @@ __device__ __forceinline__ double gauss_fused_block(const DsDev& ds, long long r
 
 // aux of a row from its stored state (used after the prefix build)
 __device__ __forceinline__ void gauss_aux_block(const DsDev& ds, long long row, int j, int lane) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   double acc = 0.0;
   for (int it = 0; it < nit; ++it) {
     const int q = q0 + it * PMDI_WF + 2 * lane;
@@ -214,8 +214,8 @@ __device__ __forceinline__ void gauss_aux_block(const DsDev& ds, long long row, 
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double cat_eval_block(const DsDev& ds, long long row, int j,
                                                  const int* xs, int lane) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   const uint32_t* cnt = ds.cnt + row * (long long)ds.Lmax * ds.Dp;
   unsigned c[8];
   int2 lv[4];
@@ -240,8 +240,8 @@ __device__ __forceinline__ double cat_eval_block(const DsDev& ds, long long row,
 
 __device__ __noinline__ void cat_add_block(const DsDev& ds, long long row, int j, const int* xs,
                                               int lane) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   uint32_t* cnt = ds.cnt + row * (long long)ds.Lmax * ds.Dp;
   for (int it = 0; it < nit; ++it) {
     const int q = q0 + it * PMDI_WF + 2 * lane;
@@ -260,8 +260,8 @@ __device__ __noinline__ void cat_add_block(const DsDev& ds, long long row, int j
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ double nb_eval_block(const DsDev& ds, long long row, int j, int n,
                                                 const int* xs, int lane, const double* lf, int T) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   const long long* S = ds.S + row * ds.Dp + q0 + 2 * lane;
   longlong2 s[4];
 #pragma unroll
@@ -281,8 +281,8 @@ __device__ __forceinline__ double nb_eval_block(const DsDev& ds, long long row, 
 // n is the size AFTER the add
 __device__ __noinline__ void nb_add_block(const DsDev& ds, long long row, int j, int n,
                                              const int* xs, int lane, const double* lf, int T) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   long long* S = ds.S + row * ds.Dp + q0 + 2 * lane;
   double acc = 0.0;
   for (int it = 0; it < nit; ++it) {
@@ -298,8 +298,8 @@ __device__ __noinline__ void nb_add_block(const DsDev& ds, long long row, int j,
 
 __device__ __forceinline__ void nb_aux_block(const DsDev& ds, long long row, int j, int n, int lane,
                                              const double* lf, int T) {
-  const int q0 = j * PMDI_FB;
-  const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+  const int q0 = j * ds.FB;
+  const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
   double acc = 0.0;
   for (int it = 0; it < nit; ++it) {
     const int q = q0 + it * PMDI_WF + 2 * lane;

@@ -16,7 +16,7 @@
 #include <vector>
 
 #include "aux_kernels.cuh"
-#include "pool_kernel.cuh"
+#include "spec_kernel.cuh"
 
 namespace {
 
@@ -63,7 +63,7 @@ struct DevBuf {
 
 struct Dataset {
   bool bound = false;
-  int type = -1, D = 0, Dp = 0, J = 0, Lmax = 0;
+  int type = -1, D = 0, Dp = 0, J = 0, Lmax = 0, FB = PMDI_FB;
   long long max_arg = 0;               // NegBinom: largest lgamma argument the sweep can form
   std::vector<uint8_t> flag;           // [Dp]
   std::vector<double> nlevels;         // categorical [D]
@@ -81,12 +81,15 @@ struct Dataset {
   DevBuf<unsigned long long> cw;
   DevBuf<int> p_refcnt, p_chosen, p_dst, p_neval, p_live, p_free, p_rowmap, p_ctr;
   DevBuf<double> p_lp;
+  DevBuf<RowInfo> p_info;
+  DevBuf<int> p_mark;
   void release() {
     x.release(); xq.release(); d_flag.release(); rc.release(); d_nlevels.release();
     mu.release(); lamn.release(); sum.release(); beta.release(); part.release(); aux.release();
     cnt.release(); S.release(); n.release(); cw.release();
     p_refcnt.release(); p_chosen.release(); p_dst.release(); p_neval.release(); p_live.release();
     p_free.release(); p_rowmap.release(); p_ctr.release(); p_lp.release();
+    p_info.release(); p_mark.release();
   }
 };
 
@@ -97,7 +100,7 @@ struct pmdi_ctx {
   long long n = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  int n_sm = 0, G = 0;
+  int n_sm = 0, G = 0, GP = 0;  // CTAs of the sweep kernel; spec engine: the first GP propose, the others evaluate
   std::vector<Dataset> ds;
   bool layout_dirty = true;
   // everything another rank has to reach (statistics, grid counter, ESS partials, log-weights, allocation
@@ -133,6 +136,10 @@ struct pmdi_ctx {
   DevBuf<long long> label_counts, pair_agree;
   DevBuf<double> rank_part;
   DevBuf<int4> pull_jobs;
+  DevBuf<unsigned char> dec;
+  DevBuf<int4> glist, elist;
+  DevBuf<int> gcnt;
+  DevBuf<unsigned long long> rows_spec;
   DevBuf<double> dbg_lp, dbg_lw, scratch_d;
   DevBuf<int> dbg_alloc, dbg_anc, scratch_i, wd_state;
   DevBuf<uint8_t> scratch_u8;
@@ -149,7 +156,7 @@ int round_up(int v, int m) { return (v + m - 1) / m * m; }
 void fill_dsdev(pmdi_ctx* c, int k, DsDev& d) {
   Dataset& s = c->ds[k];
   std::memset(&d, 0, sizeof(d));
-  d.type = s.type; d.D = s.D; d.Dp = s.Dp; d.J = s.J; d.Lmax = s.Lmax;
+  d.type = s.type; d.D = s.D; d.Dp = s.Dp; d.J = s.J; d.Lmax = s.Lmax; d.FB = s.FB;
   int nflag = 0;
   for (int q = 0; q < s.D; ++q) nflag += s.flag[q] ? 1 : 0;
   d.nflag = nflag;
@@ -168,7 +175,7 @@ void fill_pooldev(pmdi_ctx* c, int k, PoolDev& d) {
   d.cap = s.cap; d.wpf = s.wpf; d.fpw = s.fpw;
   d.refcnt = s.p_refcnt.p; d.chosen = s.p_chosen.p; d.dst = s.p_dst.p; d.n_eval = s.p_neval.p;
   d.live = s.p_live.p; d.freelist = s.p_free.p; d.rowmap = s.p_rowmap.p; d.ctr = s.p_ctr.p; d.cw = s.cw.p;
-  d.lp = s.p_lp.p;
+  d.lp = s.p_lp.p; d.info = s.p_info.p; d.mark = s.p_mark.p;
 }
 
 // x-independent row constants by cluster size n:
@@ -217,10 +224,35 @@ int build_layout(pmdi_ctx* c) {
   const int K = c->K;
   for (int k = 0; k < K; ++k)
     if (!c->ds[k].bound) return fail(3, "pmdi: dataset " + std::to_string(k) + " is not bound");
+  if (c->P % c->R != 0) return fail(1, "pmdi: particles must be a multiple of the number of ranks");
+  c->Ps = c->P / c->R;
+  // engine: the copy-on-write pool unless PMDI_ENGINE=dense asks for the dense form (every particle owns its
+  // N rows)
+  // N rows); default: the speculative single-barrier form of the pool on one GPU, the two-barrier pool when
+  // the particles are sharded over several GPUs
+  const char* eng = getenv("PMDI_ENGINE");
+  // (spec deals one row task per evaluation CTA and step: with many datasets a step has more tasks than
+  // evaluation CTAs and the two-barrier form, which uses every SM for the evaluations, measured faster - cfg3)
+  c->engine = (c->R > 1 || c->K > 4) ? 1 : 2;
+  if (eng && std::string(eng) == "dense") c->engine = 0;
+  if (eng && std::string(eng) == "pool") c->engine = 1;
+  if (eng && std::string(eng) == "spec" && c->R == 1) c->engine = 2;
+  // spec engine: role split of the grid (proposal CTAs own particle slots, evaluation CTAs own rows)
+  {
+    // proposal CTAs: one (dataset, particle) unit per warp where the SMs allow it; the rest evaluate rows
+    const int ge0 = std::max(8, c->n_sm / 8);
+    const int want = ((long long)c->Ps * c->K + 14) / 15;
+    c->GP = std::max(1, std::min(std::min(c->Ps, want), c->n_sm - ge0));
+    const int ge = std::max(1, std::min(c->n_sm - c->GP - 1, 64));
+    c->G = c->engine == 2 ? c->GP + ge + 1 : std::min(c->n_sm, c->Ps);  // + the CTA that decides on the resamplings
+  }
   int off = 0, Jmax = 1;
   long long nb_max_arg = -1;
   for (int k = 0; k < K; ++k) {
     Dataset& s = c->ds[k];
+    // a warp's share of a row: 256 features; the spec engine spreads a row over twice as many warps (latency)
+    s.FB = c->engine == 2 ? 128 : PMDI_FB;
+    s.J = (s.Dp + s.FB - 1) / s.FB;
     off = round_up(off, 16);
     off += s.Dp * (s.type == T_GAUSSIAN ? 8 : 4);
     Jmax = std::max(Jmax, s.J);
@@ -242,15 +274,13 @@ int build_layout(pmdi_ctx* c) {
   c->Ps = c->P / c->R;
   if (c->R > 1 && c->peer_base[c->rank] != nullptr)
     return fail(1, "pmdi: datasets cannot be re-bound after pmdi_ipc_export (the peers hold this layout)");
-  // engine: the copy-on-write pool unless PMDI_ENGINE=dense asks for the dense form (every particle owns its
-  // N rows)
-  const char* eng = getenv("PMDI_ENGINE");
-  c->engine = (eng && std::string(eng) == "dense") ? 0 : 1;
   if (getenv("PMDI_WATCHDOG_S")) c->wd_ns = (unsigned long long)(atof(getenv("PMDI_WATCHDOG_S")) * 1e9);
   // dense: particle slots, prototypes, the shared empty row.  pool: at most Ps*N live rows, one reservation per
   // chosen row in flight (<= Ps per dataset), the N prefix rows, the empty cluster; with several ranks a
   // resampling pulls the rows of remote ancestors before the dead local rows are freed (another Ps*N at most)
-  const long long rows = c->engine ? (long long)(c->R > 1 ? 2 : 1) * c->Ps * c->N + c->Ps + c->N + 2
+  // spec: a live row holds its child and the two ids handed out for the next step (x4)
+  const long long rows = c->engine == 2 ? 4ll * c->Ps * c->N + c->N + 4096
+                       : c->engine ? (long long)(c->R > 1 ? 2 : 1) * c->Ps * c->N + c->Ps + c->N + 2
                                    : (long long)(c->Ps + 2) * c->N;
   if (rows > 0x7fffff00ll) return fail(1, "pmdi: particles x N too large");
   const int Gmax = std::min(c->n_sm, c->Ps);
@@ -261,7 +291,7 @@ int build_layout(pmdi_ctx* c) {
   const size_t o_lw = take(sizeof(double) * (size_t)c->P);
   const size_t o_log = take((size_t)c->n * K * c->P);  // at most n_obs observation steps
   const size_t o_rankp = take(sizeof(double) * 2 * 8 * 4);
-  struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n, cw, refcnt, chosen, dst, neval, live, free_, rowmap, ctr, lp; };
+  struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n, cw, refcnt, chosen, dst, neval, live, free_, rowmap, ctr, lp, info, mark; };
   std::vector<Off> offs(K);
   for (int k = 0; k < K; ++k) {
     Dataset& s = c->ds[k];
@@ -284,9 +314,12 @@ int build_layout(pmdi_ctx* c) {
     o.part = take(c->engine ? 8 : 8 * rows * s.J); o.aux = take(8 * rows * s.J); o.n = take(4 * rows);
     if (c->engine) {
       s.cap = (int)rows;
-      o.refcnt = take(4 * rows); o.chosen = take(8 * rows); o.dst = take(8 * rows); o.neval = take(4 * rows);
+      o.refcnt = take(8 * rows); o.chosen = take(12 * rows); o.dst = take(8 * rows); o.neval = take(4 * rows);
       o.live = take(4 * rows); o.free_ = take(4 * rows); o.rowmap = take(8 * (size_t)c->Ps * c->N); o.ctr = take(64);
       o.lp = take(8 * rows);
+      if (c->engine == 2) {
+        o.info = take(2 * sizeof(RowInfo) * rows); o.mark = take(4 * rows);
+      }
     }
   }
   if (c->arena) { cudaFree(c->arena); c->arena = nullptr; }
@@ -304,10 +337,13 @@ int build_layout(pmdi_ctx* c) {
     const Off& o = offs[k];
     if (c->engine) {
       if (s.type == T_CATEGORICAL) s.cw.view(A + o.cw, rows * (size_t)s.Dp * s.wpf);
-      s.p_refcnt.view(A + o.refcnt, rows); s.p_chosen.view(A + o.chosen, 2 * rows); s.p_dst.view(A + o.dst, 2 * rows);
+      s.p_refcnt.view(A + o.refcnt, 2 * rows); s.p_chosen.view(A + o.chosen, 3 * rows); s.p_dst.view(A + o.dst, 2 * rows);
       s.p_neval.view(A + o.neval, rows); s.p_live.view(A + o.live, rows); s.p_free.view(A + o.free_, rows);
       s.p_rowmap.view(A + o.rowmap, 2 * (size_t)c->Ps * c->N); s.p_ctr.view(A + o.ctr, 16);
       s.p_lp.view(A + o.lp, rows);
+      if (c->engine == 2) {
+        s.p_info.view(A + o.info, 2 * rows); s.p_mark.view(A + o.mark, rows);
+      }
     }
     if (s.type == T_GAUSSIAN) {
       s.mu.view(A + o.mu, rows * s.Dp); s.lamn.view(A + o.lamn, rows * s.Dp);
@@ -336,8 +372,8 @@ int build_layout(pmdi_ctx* c) {
 // budget of the sweep kernel.
 int assign_units(pmdi_ctx* c) {
   const int K = c->K, P = c->Ps, N = c->N;  // the particle slots this rank holds
-  c->G = std::min(c->n_sm, P);  // one persistent CTA per SM; never a CTA without a particle
-  const int G = c->G;
+  if (c->engine != 2) c->G = std::min(c->n_sm, P);  // one persistent CTA per SM; never a CTA without a particle
+  const int G = c->engine == 2 ? c->GP : c->G;      // CTAs that own particle slots
   c->cta_off.assign(G + 1, 0);
   c->cta_units.clear();
   int max_slots = 0;
@@ -356,8 +392,14 @@ int assign_units(pmdi_ctx* c) {
   const long long MU = c->max_units, MS = max_slots;
   if (c->engine) {
     // pool engine: observation ring (2..4 deep) | lf | proposal scratch | Pi | lw | inc | unit tables
-    const long long tables = (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 + MS * 8 + MU * 8 +
-                             (MU * 11 + MS + MU * N) * 4 + 64;
+    long long tables = (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 + MS * 8 + MU * 8 +
+                       (MU * 11 + MS + MU * N) * 4 + 64;
+    if (c->engine == 2) {  // the two roles overlay one region: proposal tables | entry-list and free-id caches
+      const long long pt = (long long)(PMDI_NT / 32) * Npad * 12 + (long long)K * N * 8 + MS * 8 + MU * 8 +
+                           (MU * 8 + MS + MU * N) * 4 + 64;
+      const long long et = 2ll * SPEC_EC * 16 + (long long)K * SPEC_FC * 4 + K * 4 + 64;
+      tables = std::max(pt, et);
+    }
     const long long budget = (long long)dev_smem - 8192 - tables;  // static shared memory: the parameter block, PoolSmem
     int ring = PMDI_OBS_RING;
     while (ring > 2 && (long long)ring * c->sm_x_bytes + std::min<long long>((long long)c->lf_want * 8, 64 * 1024) > budget) --ring;
@@ -369,9 +411,11 @@ int assign_units(pmdi_ctx* c) {
     const long long lf_b = std::min<long long>((long long)c->lf_want * 8, budget - (long long)ring * c->sm_x_bytes);
     c->lf_T = (int)(lf_b / 8);
     c->item_cap = 0;
-    c->dyn_smem = (size_t)((long long)ring * c->sm_x_bytes + (long long)c->lf_T * 8 + tables);
+    c->dyn_smem = (size_t)((long long)ring * c->sm_x_bytes + (long long)c->lf_T * 8 + 8 + tables);
     CK(cudaFuncSetAttribute(k_sweep_pool, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
     CK(cudaFuncSetAttribute(k_sweep_pool_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+    CK(cudaFuncSetAttribute(k_sweep_spec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
+    CK(cudaFuncSetAttribute(k_sweep_spec_dbg, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c->dyn_smem));
   } else {
     // dense engine: 4 observation buffers | lf | proposal scratch | Pi | lw | inc | part x2 | items x2 | unit tables
     const long long fixed = 4LL * c->sm_x_bytes + (long long)(PMDI_NT / 32) * Npad * 8 + (long long)K * N * 8 +
@@ -414,7 +458,7 @@ int fill_params(pmdi_ctx* c) {
   sp.engine = c->engine; sp.obs_ring = c->obs_ring; sp.wd_ns = c->wd_ns;
   sp.proto_base = c->engine ? 0 : (long long)c->Ps * c->N;
   sp.rank_part = c->rank_part.p;
-  sp.K = c->K; sp.N = c->N; sp.P = c->P; sp.n_obs = (int)c->n; sp.G = c->G;
+  sp.K = c->K; sp.N = c->N; sp.P = c->P; sp.n_obs = (int)c->n; sp.G = c->G; sp.GP = c->GP;
   sp.R = c->R; sp.rank = c->rank; sp.Ps = c->Ps; sp.slot0 = c->rank * c->Ps;
   for (int r = 0; r < 8; ++r) sp.peer_delta[r] = c->peer_delta[r];
   sp.Jmax = c->Jmax;
@@ -504,6 +548,7 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   for (auto* b : dl) b->release();
   c->lab.release(); c->alloc_log.release(); c->copies.release(); c->bar.release();
   c->rows_eval.release(); c->phase_ns.release(); c->scratch_u8.release();
+  c->dec.release(); c->rows_spec.release(); c->glist.release(); c->elist.release(); c->gcnt.release();
   c->rows_ref.release(); c->trace.release(); c->wd_state.release(); c->pull_jobs.release(); c->rank_part.release();
   c->label_counts.release(); c->pair_agree.release();
   for (int r = 0; r < c->R; ++r)
@@ -733,6 +778,19 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   CK(c->cur_at.ensure(steps));
   CK(c->rows_ref.ensure(PMDI_MAX_K)); CK(c->label_counts.ensure((size_t)N * K)); CK(c->pair_agree.ensure(std::max(npairs, 1)));
   sp.rows_ref = c->rows_ref.p;
+  CK(c->dec.ensure(steps)); CK(c->rows_spec.ensure(PMDI_MAX_K));
+  CK(cudaMemsetAsync(c->rows_spec.p, 0, 8 * PMDI_MAX_K, st));
+  sp.dec = c->dec.p; sp.rows_spec = c->rows_spec.p;
+  if (c->engine == 2) {  // the live-row list: at most one entry per (particle slot, label) and dataset
+    const long long lcap = (long long)K * ((long long)c->Ps * N + N + 2);
+    CK(c->glist.ensure(lcap)); CK(c->gcnt.ensure(4));
+    CK(c->elist.ensure(2 * (size_t)(c->G - c->GP - 1) * lcap));
+    CK(cudaMemsetAsync(c->gcnt.p, 0, 16, st));
+    sp.glist = c->glist.p; sp.gcnt = c->gcnt.p; sp.elist = c->elist.p; sp.lcap = lcap;
+    // cached free ids per E-CTA and dataset: never more than a quarter of the pool over all E-CTAs
+    const long long cap = c->ds[0].cap, ge = c->G - c->GP - 1;
+    sp.fc_target = (int)std::max<long long>(8, std::min<long long>(SPEC_FC / 2, cap / (4 * ge)));
+  }
   sp.pull_jobs = nullptr;
   if (c->engine && c->R > 1) {
     CK(c->pull_jobs.ensure((size_t)K * c->Ps * N));
@@ -802,7 +860,14 @@ int pmdi_sweep_run(pmdi_ctx* c) {
   k_prefix_build<<<dim3((maxDp + 127) / 128, N, K), 128, 0, st>>>(sp, c->members.p, c->mem_off.p);
   k_proto_aux<<<dim3(N, K), 256, 0, st>>>(sp);
   void* args[] = {(void*)&c->sp};
-  if (c->engine) {
+  if (c->engine == 2) {
+    k_spec_init<<<K, 1024, 0, st>>>(sp);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, st));
+    const bool dbg = (c->sweep_flags & (PMDI_SWEEP_DEBUG | PMDI_SWEEP_TIME_PHASES)) || sp.trace;
+    CK(cudaLaunchCooperativeKernel(dbg ? (const void*)k_sweep_spec_dbg : (const void*)k_sweep_spec, dim3(c->G), dim3(PMDI_NT), args,
+                                   c->dyn_smem, st));
+  } else if (c->engine) {
     k_pool_init<<<K, 1024, 0, st>>>(sp);
     CK(cudaGetLastError());
     CK(cudaEventRecord(c->ev1, st));
@@ -834,13 +899,14 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   const int steps = c->sp.steps;
   int err = 0;
   long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  unsigned long long rows[PMDI_MAX_K], rref[PMDI_MAX_K];
+  unsigned long long rows[PMDI_MAX_K], rref[PMDI_MAX_K], rspec[PMDI_MAX_K];
   std::vector<unsigned long long> phase(8 * (size_t)c->G, 0ull);
   long long pstar = 0;
   CK(cudaMemcpyAsync(&err, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(counters, c->counters.p, sizeof(counters), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(rows, c->rows_eval.p, sizeof(rows), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(rref, c->rows_ref.p, sizeof(rref), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(rspec, c->rows_spec.p, sizeof(rspec), cudaMemcpyDeviceToHost, st));
   if (o->label_counts)
     CK(cudaMemcpyAsync(o->label_counts, c->label_counts.p, sizeof(int64_t) * N * K, cudaMemcpyDeviceToHost, st));
   if (o->pair_agree && K > 1)
@@ -902,8 +968,9 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
     dense += (long long)steps * P * N * c->ds[k].D;
     o->rows_evaluated[k] = (int64_t)rows[k];
     o->rows_referenced[k] = (int64_t)rref[k];
+    o->rows_computed[k] = c->engine == 2 ? (int64_t)rspec[k] : (int64_t)rows[k];
   }
-  for (int k = K; k < 8; ++k) { o->rows_evaluated[k] = 0; o->rows_referenced[k] = 0; }
+  for (int k = K; k < 8; ++k) { o->rows_evaluated[k] = 0; o->rows_referenced[k] = 0; o->rows_computed[k] = 0; }
   o->engine = c->engine;
   o->n_evals = ev;
   o->n_evals_dense = dense;

@@ -29,6 +29,7 @@ enum { DRAW_ALLOC = 0, DRAW_RESAMP = 1, DRAW_SHUFFLE = 2, DRAW_SELECT = 3, DRAW_
 struct DsDev {
   int type, D, Dp, J;
   int Lmax, all_on, x_off /* byte offset of this dataset's row in the smem staging area */, nflag;
+  int FB, pad0;         /* features per block (one warp's share of a row; aux and J are per block): 256, spec engine 128 */
   const void* x;        /* [n_obs][Dp]: f64 (Gaussian) or i32 (others), row-major        */
   const void* xstage;   /* what the sweep stages: x, or x with the feature flags folded in */
   const uint8_t* flag;  /* [Dp], padded features are 0                                    */
@@ -49,12 +50,20 @@ struct DsDev {
  * refer to it, and resampling permutes row maps instead of moving statistics.  Row cap-1 is the
  * EMPTY cluster (never written; every unoccupied label of every particle refers to it).
  */
+/* spec engine (spec_kernel.cuh): what the proposals read about a row at one observation step */
+struct RowInfo {
+  double lp;   /* predictive of the step's observation                                         */
+  int child;   /* the row that holds (this row + the step's observation)                       */
+  int pad;
+};
+
 struct PoolDev {
   int cap;           /* physical rows, row cap-1 = the empty cluster                         */
   int wpf, fpw;      /* categorical packing: 64-bit words per feature, count fields per word  */
   int pad;
-  int* refcnt;       /* [cap] (particle, label) references of a row                          */
-  int* chosen;       /* [2][cap] by step parity: particles that chose the row this step       */
+  int* refcnt;       /* [cap] (particle, label) references of a row ([2][cap] in the spec engine)   */
+  int* chosen;       /* [2][cap] by step parity: particles that chose the row this step ([3][cap] by step mod 3
+                        in the spec engine)                                                    */
   int* dst;          /* [2][cap] by step parity: row id reserved for the split of the row     */
   int* n_eval;       /* [cap] cluster size the row's current predictive was evaluated with    */
   int* live;         /* [cap] list of live rows (live[0] = the empty cluster)                 */
@@ -63,9 +72,11 @@ struct PoolDev {
   int* ctr;          /* [0] live rows, [1] free rows                                          */
   unsigned long long* cw; /* [cap][Dp][wpf] packed categorical counts                          */
   double* lp;        /* [cap] this step's predictive of every live row (E phase -> P phase)       */
+  RowInfo* info;     /* spec engine: [2][cap] by step parity                                      */
+  int* mark;         /* spec engine: [cap] rows a resampling must keep although nobody refers to them */
 };
 
-struct SweepParams {
+struct __attribute__((aligned(16))) SweepParams {
   int K, N, P, n_obs, n1, steps;
   int G, flags;
   /* particle sharding: R ranks (one GPU each), this one holds slots [slot0, slot0 + Ps) of the P global
@@ -74,7 +85,16 @@ struct SweepParams {
   long long peer_delta[8];
   DsDev ds[PMDI_MAX_K];
   PoolDev pd[PMDI_MAX_K];
-  int engine;             /* 0 dense (sweep_kernel.cuh), 1 pool (pool_kernel.cuh)            */
+  int engine;             /* 0 dense (sweep_kernel.cuh), 1 pool (pool_kernel.cuh), 2 spec (spec_kernel.cuh) */
+  int GP;                 /* spec engine: CTAs 0..GP-1 propose, GP..G-1 evaluate               */
+  unsigned char* dec;     /* spec engine: [steps] resampling decision after each step (0 unknown, 1 no, 2 yes) */
+  unsigned long long* rows_spec; /* [K] row evaluations actually performed (live rows and their children) */
+  int4* glist;            /* spec engine: [lcap] the live-row list a set-up / resampling leaves for the E-CTAs */
+  int* gcnt;              /*              its length                                             */
+  int4* elist;            /* spec engine: [2][E-CTAs][lcap] the E-CTAs' copies of the list beyond shared memory */
+  long long lcap;
+  int fc_target;          /* spec engine: free-row ids an E-CTA keeps cached per dataset        */
+  int pad1;
   int obs_ring;           /* depth of the shared-memory observation ring (2..4)              */
   long long proto_base;   /* first row of the rho-prefix prototypes (dense: Ps*N, pool: 0)   */
   unsigned long long wd_ns; /* watchdog of the in-kernel waits                               */

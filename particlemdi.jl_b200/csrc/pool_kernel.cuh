@@ -236,8 +236,8 @@ __device__ __noinline__ void pool_eval_rows(const SweepParams& sp, PoolSmem& sm,
         const unsigned xo = (unsigned)ds.x_off;
 #pragma unroll 1
         for (int j = wj; j < ds.J; j += jq) {
-          const int q0 = j * PMDI_FB;
-          const int nit = min(PMDI_FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
+          const int q0 = j * ds.FB;
+          const int nit = min(ds.FB / PMDI_WF, (ds.Dp - q0) / PMDI_WF);
           const int fo = q0 + 2 * lane;
           double vs = 0.0, v;
           if (ds.type == T_GAUSSIAN) {
@@ -1126,7 +1126,7 @@ __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long
       cluster_n[idx] = (ls >= 0 && ls < sp.Ps) ? sp.ds[k].n[(long long)ls * N + m] : -1;
     }
   }
-  if (cluster_n && sp.engine == 1) {
+  if (cluster_n && sp.engine >= 1) {
     const int ev = (int)sp.counters[2];
 #pragma unroll 1
     for (size_t idx = t; idx < (size_t)K * P * N; idx += NT) {

@@ -23,6 +23,9 @@ ev = [(int(a), int(b), int(c)) for a, b, c in ev]
 t0 = min(c for _, _, c in ev)
 names = {40: "top", 41: "svc", 42: "P[", 43: "ld", 44: "exp", 45: "cum", 46: "lab", 47: "atom", 48: "]P", 49: "arrB2",
          50: "B2", 51: "res", 52: "ess", 53: "E[", 54: "meta", 55: "]E", 56: "arrB1"}
+if os.environ.get("PMDI_ENGINE", "spec") == "spec":
+    names = {40: "top", 41: "dec", 42: "P[", 43: "ld", 44: "exp", 45: "cum", 46: "lab", 47: "]P", 49: "C[", 48: "]C",
+             51: "fix", 52: "eval", 56: "arr", 60: "f.b", 61: "f.ld", 62: "f.scan", 63: "e.in", 64: "e.blk", 65: "e.sync", 66: "e.fin"}
 for w in range(16):
     row = [(tag, c - t0) for ww, tag, c in ev if ww == w]
     print("w%02d" % w, " ".join(f"{names.get(tag, tag)}@{c}" for tag, c in row))

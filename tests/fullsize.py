@@ -62,7 +62,7 @@ def compare(cfg, sweep_fn, seed=77):
     }
     if "cluster_n" in got and (got["cluster_n"] >= 0).all():
         out["cluster_n_mismatch"] = int((got["cluster_n"] != ref["cluster_n"]).sum())
-    if got.get("engine") == "pool":
+    if got.get("engine") in ("pool", "spec"):
         out["rows_evaluated"] = int(sum(got["rows_evaluated"])) - int(got["rows_evaluated_ahead"])
         out["rows_evaluated_ahead_of_resampling"] = int(got["rows_evaluated_ahead"])
     if cfg["debug"]:
