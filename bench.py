@@ -9,7 +9,12 @@ NegBinom 1000 features, N=20, 256 particles, rho=0.25).
   python bench.py --gpus N --steps K --warmup W          # this repo's CUDA path
   python bench.py --impl reference ...                   # the restated reference on the host CPU
 
-Prints ONE JSON line (contract in the task statement).
+Prints ONE JSON line (contract in the task statement).  Besides the headline workload the line
+carries: `parity` (one sweep checked against the oracle before anything is timed - the oracle is
+used as the checker only), at N = 1 a `cfg4` block (the 20,000-cell configuration the north-star
+puts its targets on: default engine and the dense engine's HBM roofline) and `pmdi_end_to_end`
+(MCMC iterations per second through pmdi() with the host-side hyper-parameter updates), at N > 1 a
+`cfg4_strong` block (1,024 particles sharded over the N GPUs).
 """
 from __future__ import annotations
 
@@ -18,11 +23,13 @@ import json
 import os
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
@@ -34,19 +41,24 @@ BURN_IN = 8
 
 METRIC = "particle*cluster*feature evals/sec (dense count P*N*sum_k D_k per observation step)"
 UNIT = "evals/s"
-PHASES = ["warp_idle_or_waiting", "items(predictive+fused add)", "proposal+fold+arrive", "unused3", "unused4", "unused5", "resample"]
+PHASES = {
+    "spec": ["wait_at_barrier", "evaluate(E-CTAs)", "propose+commit(P-CTAs)", "outcome_bookkeeping(E-CTAs)", "-", "-", "resample"],
+    "pool": ["wait_at_barrier_B1", "evaluate", "propose", "resolve", "wait_at_barrier_B2", "-", "resample"],
+    "dense": ["warp_idle_or_waiting", "items(predictive+fused add)", "proposal+fold+arrive", "-", "-", "-", "resample"],
+}
+LAUNCHES = {"spec": 7, "pool": 7, "dense": 8}  # kernels per sweep: init, prefix lists/build/aux, (pool init | broadcast+empty), sweep, finish
 
-# algorithmic bytes per eval / per add at the reference's widths and as stored
+# algorithmic bytes per predictive term / per feature of an added cluster at the reference's widths
+#  and as stored on the device
 READ_B = {0: 16, 1: 8, 2: 8}
 ADD_B = {0: 64, 1: 16, 2: 16}
-READ_B_STORED = {0: 16, 1: 4, 2: 8}
-ADD_B_STORED = {0: 56, 1: 8, 2: 16}
+READ_B_STORED = {0: 16, 1: 8, 2: 8}
+ADD_B_STORED = {0: 64, 1: 16, 2: 16}
 
 
-def make_workload(name, seed_shift=0, particles=None):
+def make_workload(name, seed_shift=0, particles=None, **over):
     import pmdi_b200  # noqa: F401
     from pmdi_b200 import synth
-    over = {}
     if particles:
         over["P"] = particles
     cfg = synth.make_config(name, **over)
@@ -60,6 +72,15 @@ def make_workload(name, seed_shift=0, particles=None):
 def dense_evals_per_sweep(cfg):
     steps = cfg["n"] - cfg["n1"] + 1
     return steps * cfg["P"] * cfg["N"] * sum(d.shape[1] for d in cfg["data"])
+
+
+def common_config(cfg, burn):
+    """The keys BOTH arms print under `config` (the driver compares them)."""
+    return {"workload": cfg["name"], "n_obs": cfg["n"], "K": cfg["K"], "N": cfg["N"], "particles": cfg["P"],
+            "rho": cfg["rho"], "features": [int(d.shape[1]) for d in cfg["data"]],
+            "observation_steps_per_sweep": cfg["n"] - cfg["n1"] + 1,
+            "chain_state": f"settled: {burn} untimed burn-in sweeps from the random initial allocation",
+            "l2": "256 MiB buffer written between timed sweeps (L2 flush)"}
 
 
 class ClockSampler:
@@ -113,6 +134,9 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+# --------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the oracle port on the host cores (the one place it is the thing timed)
+# --------------------------------------------------------------------------------------------------
 def run_reference(args):
     """The reference's own algorithm on the host CPU: the C++ restatement in its literal,
     de-duplicated form (copy-on-write cluster pool + fprob cache, src/pmdi.jl:131-146,223-310),
@@ -149,23 +173,20 @@ def run_reference(args):
     dense = dense_evals_per_sweep(cfg)
     val = dense * args.steps / total
     sample = (f"{args.steps} full sweeps of {args.workload} (n={n}, {n - cfg['n1'] + 1} observation steps "
-              f"each) after {BURN_IN} burn-in sweeps, de-duplicated literal mode, g++ -O3, 1 thread")
+              f"each) after {n_burn} burn-in sweeps, de-duplicated literal mode, g++ -O3, 1 thread")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": args.workload, "n_obs": n, "K": cfg["K"], "N": cfg["N"],
-                   "particles": cfg["P"], "rho": cfg["rho"],
-                   "chain_state": f"settled: {n_burn} untimed burn-in sweeps from the random initial allocation"
-                                  + ("" if n_burn == BURN_IN else f" (cut from {BURN_IN} by the 150 s bound)"),
-                   "burn_in_sweep_ms": [round(1e3 * v, 1) for v in burn],
+        "config": common_config(cfg, BURN_IN),
+        "detail": {"burn_in_sweeps_run": n_burn, "burn_in_sweep_ms": [round(1e3 * v, 1) for v in burn],
                    "note": "restated reference (C++), not Julia: julia is not installed in this image; "
                            "value counts the DENSE evals the sweep stands for, the reference evaluates "
                            "only unique clusters (calc_logprob calls in last sweep: %d)" % r["n_ops"]},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "mcmc_iters_per_s": args.steps / total,
+        "mcmc_sweeps_per_s": args.steps / total,
     }
     print(json.dumps(line), flush=True)
 
@@ -202,6 +223,193 @@ def cpu_baseline_leg(cfg, budget_s=6.0):
             "calc_logprob_calls_last_sweep": r["n_ops"]}
 
 
+# --------------------------------------------------------------------------------------------------
+# this repo's arm
+# --------------------------------------------------------------------------------------------------
+class Runner:
+    """One workload on this rank's GPU (all ranks together when the particles are sharded)."""
+
+    def __init__(self, cfg, world, rank, local, stream, flush, engine=None):
+        import torch.distributed as dist
+        from pmdi_b200 import capi
+        self.cfg, self.world, self.rank, self.flush, self.dist = cfg, world, rank, flush, dist
+        old = os.environ.get("PMDI_ENGINE")
+        if engine:
+            os.environ["PMDI_ENGINE"] = engine
+        try:
+            self.ctx = capi.Context(cfg["data"], cfg["types"], cfg["N"], cfg["P"], device=local, rank=rank, n_ranks=world)
+            if world > 1:
+                self.ctx.connect()
+            capi._check(capi.lib().pmdi_ctx_set_stream(self.ctx.h, stream.cuda_stream))
+            # the engine is fixed when the arena is laid out: force that now, while the variable is set
+            self.ctx.upload(cfg["hy"]["s"], np.arange(cfg["n"]) + 1, cfg["n1"], cfg["hy"]["Pi"], cfg["hy"]["phi"])
+        finally:
+            if engine:
+                if old is None:
+                    os.environ.pop("PMDI_ENGINE", None)
+                else:
+                    os.environ["PMDI_ENGINE"] = old
+        self.stream = stream
+        self.s = cfg["hy"]["s"]
+        self.it = 0
+        self.engine = None
+
+    def _sync_ranks(self):
+        """With several ranks every rank's grid counter must be reset (upload) before any rank's
+        kernel starts to arrive on it (include/pmdi_cuda.h)."""
+        if self.world > 1:
+            self.dist.barrier()
+
+    def chain(self, sweeps, orders, record=None):
+        """Untimed sweeps through the same upload -> L2 flush -> run -> download sequence as the timed ones."""
+        cfg, hy = self.cfg, self.cfg["hy"]
+        for _ in range(sweeps):
+            self.ctx.upload(self.s, orders[self.it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=self.it,
+                            logweight_init=0.0 if self.it == 0 else 1.0)
+            self._sync_ranks()
+            self.flush.zero_()
+            self.ctx.run()
+            r = self.ctx.download()
+            self.s = r["s"]
+            self.engine = r["engine"]
+            if record is not None:
+                record.append(r["sweep_kernel_ms"])
+            self.it += 1
+
+    def timed(self, steps, orders):
+        """K sweeps back to back on the device, CUDA events on the launching stream.  Each sweep's inputs
+        (allocations, the shuffled order, Pi, Phi: a few KB) are handed to the context right before its run;
+        the allocations are those of the chain so far, so there is no device->host read in the region."""
+        import torch
+        cfg, hy = self.cfg, self.cfg["hy"]
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record(self.stream)
+        for t in range(steps):
+            self.ctx.upload(self.s, orders[self.it + t], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=self.it + t,
+                            logweight_init=1.0)
+            self._sync_ranks()
+            self.flush.zero_()
+            self.ctx.run()
+            ev[t + 1].record(self.stream)
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        self.ctx.download()
+        return ev[0].elapsed_time(ev[steps]), [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+
+    def per_launch(self, steps, orders):
+        """The same sweeps once more, one at a time: kernel time per launch (CUDA events inside the library,
+        on the same stream) and the work counters."""
+        cfg, hy, K = self.cfg, self.cfg["hy"], self.cfg["K"]
+        do = self.ctx.sweep_sharded if self.world > 1 else self.ctx.sweep
+        out = dict(kms=[], rows=np.zeros(K), rows_computed=np.zeros(K), resamples=0, copies=0, evals=0, remote=0,
+                   rows_ref=np.zeros(K), rows_added=np.zeros(K))
+        r = None
+        for t in range(steps):
+            self.flush.zero_()
+            r = do(self.s, orders[self.it + t], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=self.it + t,
+                   logweight_init=1.0, time_phases=(t == steps - 1))
+            if t < steps - 1:  # the last launch runs the instrumented kernel (phase timers): not a kernel time
+                out["kms"].append(r["sweep_kernel_ms"])
+            out["rows"] += np.array(r["rows_evaluated"][:K], dtype=float)
+            out["rows_computed"] += np.array(r["rows_computed"][:K], dtype=float)
+            out["rows_ref"] += np.array(r["rows_referenced"][:K], dtype=float)
+            out["rows_added"] += np.array(r["rows_added"][:K], dtype=float)
+            out["resamples"] += r["n_resamples"]
+            out["copies"] += r["n_copies"]
+            out["evals"] += r["n_evals"]
+            out["remote"] += r["n_remote_rows"]
+        out["phase_ms"], out["phase_ms_max"], out["engine"] = r["phase_ms"], r["phase_ms_max"], r["engine"]
+        return out
+
+    def e2e(self, steps, orders):
+        """End to end through pmdi_sweep() with host buffers, allocations chained sweep to sweep."""
+        import torch
+        cfg, hy = self.cfg, self.cfg["hy"]
+        do = self.ctx.sweep_sharded if self.world > 1 else self.ctx.sweep
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        s2 = self.s
+        for t in range(steps):
+            r2 = do(s2, orders[self.it + t], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=self.it + t,
+                    logweight_init=1.0)
+            s2 = r2["s"]
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+        return time.perf_counter() - t0
+
+    def close(self):
+        self.ctx.close()
+
+
+def roofline(cfg, pl, steps, k_ms, world, peak, peak_src, traffic, engine):
+    """HBM roofline of the sweep kernel by ALGORITHMIC bytes: what the reference's own algorithm has to
+    move - every distinct cluster's predictive once per observation (16|8|8 B per feature at the
+    reference's widths) and the add of every chosen cluster (64|16|16 B per feature, read + write)."""
+    K, types = cfg["K"], cfg["types"]
+    D = [int(d.shape[1]) for d in cfg["data"]]
+    steps_obs = cfg["n"] - cfg["n1"] + 1
+    # adds: dense - one per (particle, dataset) and step; copy-on-write - one per DISTINCT chosen cluster and step.
+    # A row that is added and evaluated in one pass is charged the add only (64 B per feature, not 64 + 16).
+    rows, adds = pl["rows"] / steps, pl["rows_added"] / steps
+    alg = sum((rows[k] - min(rows[k], adds[k])) * D[k] * READ_B[types[k]] + adds[k] * D[k] * ADD_B[types[k]] for k in range(K))
+    alg_unfused = sum(rows[k] * D[k] * READ_B[types[k]] + adds[k] * D[k] * ADD_B[types[k]] for k in range(K))
+    moved = None
+    if engine == "spec":  # what this engine really reads and writes: every live row and its child, every step
+        moved = sum(pl["rows_computed"][k] / steps / 2.0 * D[k] * ADD_B_STORED[types[k]] for k in range(K))
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    out = {
+        "bound": "hbm", "kernel": {"spec": "k_sweep_spec", "pool": "k_sweep_pool", "dense": "k_sweep"}[engine] +
+                                  " (persistent, one launch per sweep)" + ("" if world == 1 else "; rank 0's launch and particles"),
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+        "traffic": traffic, "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
+        "achieved_if_add_and_eval_counted_separately": alg_unfused / (k_ms * 1e-3) / 1e9,
+        "us_per_observation_step": 1e3 * k_ms / steps_obs,
+    }
+    if moved is not None:
+        out["device_bytes_model_per_launch"] = moved
+    if engine != "dense":
+        out["note"] = ("the copy-on-write engines evaluate each DISTINCT cluster once per observation, as the reference does: "
+                       "the bytes are ~1e2-1e3 x fewer than the dense form's and the sweep is a chain of dependent per-"
+                       "observation phases bound by latency (us_per_observation_step), not by HBM; `frac` is reported because "
+                       "the contract asks for it - the dense engine's figure, where the HBM roofline is the binding one, is "
+                       "under cfg4.dense_engine")
+    return out
+
+
+def parity_block(cfg_name, world, rank, local, stream, flush, particles=None, **over):
+    """One sweep of the workload checked against the oracle (the checker, never the thing measured):
+    allocations, selected particle, resampling count bit-exact, log-weights to 1e-5."""
+    import fullsize
+    cfg = make_workload(cfg_name, particles=particles, **over)
+    cfg.update(chain=0, debug=False)
+    run = Runner(cfg, world, rank, local, stream, flush)
+    hy = cfg["hy"]
+
+    def sweep_fn(s, order, it, lw0, debug):
+        do = run.ctx.sweep_sharded if world > 1 else run.ctx.sweep
+        return do(s, order, cfg["n1"], hy["Pi"], hy["phi"], seed=77, it=it, logweight_init=lw0)
+    if rank == 0:
+        out = fullsize.compare(cfg, sweep_fn)
+        ok = (out["s_mismatch"] == 0 and out["p_star_equal"] and out["n_resamples"][0] == out["n_resamples"][1]
+              and out["logweight_max_rel"] <= 1e-5)
+        res = {"checked": f"one sweep of {cfg_name} (P={cfg['P']}, n={cfg['n']}) from the random initial allocation vs the "
+                          "oracle's de-duplicated corrected mode", "ok": bool(ok),
+               "allocation_mismatches": out["s_mismatch"], "draws": out["draws"], "p_star_equal": out["p_star_equal"],
+               "n_resamples_gpu_vs_oracle": out["n_resamples"], "logweight_max_rel": out["logweight_max_rel"],
+               "cluster_size_mismatches": out.get("cluster_n_mismatch"), "oracle_s": out["oracle_s"]}
+    else:  # the other ranks run the same sweep (same arguments), rank 0 checks
+        rng = np.random.default_rng(77)
+        order = rng.permutation(cfg["n"]) + 1
+        sweep_fn(hy["s"], order, 0, 0.0, False)
+        res = None
+    run.close()
+    return res
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -216,198 +424,190 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    stream = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    traffic_db = []
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath))
+        traffic_db = tj if isinstance(tj, list) else [tj]
+
+    def traffic_for(workload, P, engine):
+        for e in traffic_db:
+            if e.get("workload") == workload and e.get("particles") == P and e.get("engine", "dense") == engine and world == 1:
+                return e.get("dram_bytes_per_launch")
+        return None
+
+    # ---------------------------------------------------------------- parity first (checker only)
+    parity = None if args.no_parity else parity_block(
+        args.workload, world, rank, local, stream, flush,
+        particles=(args.particles or make_workload(args.workload)["P"]) * world)
+
+    # ---------------------------------------------------------------- the headline workload
     # Particles are sharded over the GPUs: weak scaling = the configuration's particle
     # count PER GPU, so the job has P * world particles; every rank passes identical arguments.
     base = make_workload(args.workload, particles=args.particles)
     cfg = make_workload(args.workload, particles=base["P"] * world)
-    hy, n, K, N, P = cfg["hy"], cfg["n"], cfg["K"], cfg["N"], cfg["P"]
-    ctx = capi.Context(cfg["data"], cfg["types"], N, P, device=local, rank=rank, n_ranks=world)
-    if world > 1:
-        ctx.connect()
-    stream = torch.cuda.current_stream()
-    capi._check(capi.lib().pmdi_ctx_set_stream(ctx.h, stream.cuda_stream))
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+    n, K, N, P = cfg["n"], cfg["K"], cfg["N"], cfg["P"]
     rng = cfg["rng"]
-    orders = [rng.permutation(n) + 1 for _ in range(BURN_IN + args.warmup + args.steps)]
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def ranks_ready():
-        """With several ranks every rank's grid counter must be reset (upload) before any rank's
-        kernel starts to arrive on it (include/pmdi_cuda.h)."""
-        if world > 1:
-            dist.barrier()
-
-    # ---------------------------------------------------------------- device-resident timing
+    orders = [rng.permutation(n) + 1 for _ in range(BURN_IN + args.warmup + 3 * args.steps + 2)]
+    run = Runner(cfg, world, rank, local, stream, flush)
     # the clock sampler starts BEFORE the warm-up: nvidia-smi's NVML start-up stalls launches on the
     # device for a while and must not land inside the timed region; it keeps sampling through it
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(1.5)
-    # Warm-up = the SAME step as the timed one (upload -> L2 flush -> run), so that one-time costs
-    # (module loading of the flush kernel, first cooperative launch, buffer growth) stay outside
-    # the timed region; allocations are chained sweep to sweep as in pmdi().
-    s = hy["s"]
     burn_ms = []
-    for it in range(BURN_IN + args.warmup):
-        ctx.upload(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
-                   logweight_init=0.0 if it == 0 else 1.0)
-        ranks_ready()
-        flush.zero_()
-        ctx.run()
-        r = ctx.download()
-        s = r["s"]
-        if it < BURN_IN:
-            burn_ms.append(r["sweep_kernel_ms"])
+    run.chain(BURN_IN, orders, burn_ms)
+    run.chain(args.warmup, orders)   # warm-up = the SAME step as the timed one
     if rank == 0:
         sampler.mark()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # Timed region: K sweeps back to back on the device.  Each sweep's inputs (allocations, the
-    # shuffled order, Pi, Phi: a few KB) are handed to the context right before its run; the
-    # allocations are those of the warm-up chain, so there is no device->host read in the region.
-    step_ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    e0.record(stream)
-    step_ev[0].record(stream)
-    for t in range(args.steps):
-        it = BURN_IN + args.warmup + t
-        ctx.upload(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
-                   logweight_init=1.0)
-        ranks_ready()
-        flush.zero_()
-        ctx.run()
-        step_ev[t + 1].record(stream)
-    e1.record(stream)
-    barrier()
-    dev_ms = e0.elapsed_time(e1)
-    step_ms = [step_ev[i].elapsed_time(step_ev[i + 1]) for i in range(args.steps)]
-    r = ctx.download()
+    dev_ms, step_ms = run.timed(args.steps, orders)
     clocks = sampler.stop() if rank == 0 else None
-
-    do_sweep = ctx.sweep_sharded if world > 1 else ctx.sweep
-    # per-launch kernel time + work counters: one more pass, sweep by sweep (untimed region)
-    kms, rows_k, resamples, ncopies, evals, remote_rows = [], np.zeros(K), 0, 0, 0, 0
-    for t in range(args.steps):
-        it = BURN_IN + args.warmup + t
-        flush.zero_()
-        r = do_sweep(s, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
-                     logweight_init=1.0, time_phases=(t == args.steps - 1))
-        kms.append(r["sweep_kernel_ms"])
-        rows_k += np.array(r["rows_evaluated"][:K], dtype=float)
-        resamples += r["n_resamples"]
-        ncopies += r["n_copies"]
-        evals += r["n_evals"]
-        remote_rows += r["n_remote_rows"]
-    phase_ms, phase_ms_max = r["phase_ms"], r["phase_ms_max"]
-
-    # ---------------------------------------------------------------- end to end (host buffers)
-    barrier()
-    t0 = time.perf_counter()
-    s2 = s
-    for t in range(args.steps):
-        it = BURN_IN + args.warmup + t
-        r2 = do_sweep(s2, orders[it], cfg["n1"], hy["Pi"], hy["phi"], seed=cfg["seed"], it=it,
-                      logweight_init=1.0)
-        s2 = r2["s"]  # the next sweep starts from these allocations, as in pmdi()
-    barrier()
-    e2e_s = time.perf_counter() - t0
+    pl = run.per_launch(args.steps, orders)
+    e2e_s = run.e2e(args.steps, orders)
+    run.close()
 
     dense = dense_evals_per_sweep(cfg)
-    steps_obs = n - cfg["n1"] + 1
     t_dev = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t_dev, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(t_dev[0]), float(t_dev[1])
-    # `dense` already counts the whole job (P = particles per GPU x GPUs)
-    value = dense * args.steps / (dev_ms * 1e-3)
+    value = dense * args.steps / (dev_ms * 1e-3)       # `dense` already counts the whole job
     e2e_val = dense * args.steps / (e2e_ms * 1e-3)
-    evals_t = torch.tensor([float(evals), float(remote_rows)], dtype=torch.float64, device="cuda")
+    evals_t = torch.tensor([float(pl["evals"]), float(pl["remote"])], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(evals_t, op=dist.ReduceOp.SUM)
     evals, remote_rows = float(evals_t[0]), float(evals_t[1])
 
+    # ---------------------------------------------------------------- the other blocks
+    cfg4 = cfg4_block(world, rank, local, stream, flush, peak, peak_src, traffic_for) if not args.no_cfg4 else None
+    pmdi_e2e = pmdi_block(local) if (world == 1 and rank == 0 and not args.no_pmdi) else None
+
     if rank == 0:
-        D = [d.shape[1] for d in cfg["data"]]
-        types = cfg["types"]
-        alg = sum(rows_k[k] * D[k] * READ_B[types[k]] for k in range(K)) / args.steps + \
-            sum(steps_obs * (P // world) * D[k] * ADD_B[types[k]] for k in range(K))
-        alg_stored = sum(rows_k[k] * D[k] * READ_B_STORED[types[k]] for k in range(K)) / args.steps + \
-            sum(steps_obs * (P // world) * D[k] * ADD_B_STORED[types[k]] for k in range(K))
-        k_ms = float(np.mean(kms))
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        traffic = None
-        tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
-            tj = json.load(open(tpath))
-            for e in (tj if isinstance(tj, list) else [tj]):  # ncu captures, one entry per workload
-                if e.get("workload") == args.workload and e.get("particles") == P and world == 1:
-                    traffic = e.get("dram_bytes_per_launch")
-        achieved = alg / (k_ms * 1e-3) / 1e9
-        h2d = n * K * 8 + n * 4 + N * K * 8 + max(1, K * (K - 1) // 2) * 8
-        d2h = n * K * 8 + P * 8 + K * P * N * 8 + 8 + 4 + 32 + 64 + 64
+        engine = pl["engine"]
+        k_ms = float(np.mean(pl["kms"]))
+        h2d = n * K * 8 + n * 8 + N * K * 8 + max(1, K * (K - 1) // 2) * 8
+        d2h = n * K * 8 + P * 8 + K * P * N * 8 + N * K * 8 + max(1, K * (K - 1) // 2) * 8 + 8 + 4 + 64 * 6
+        roof = roofline(cfg, pl, args.steps, k_ms, world, peak, peak_src, traffic_for(args.workload, P, engine), engine)
+        roof["kernel_share_of_step"] = k_ms / (dev_ms / args.steps)
+        roof["warp_ms_mean_over_ctas"] = dict(zip(PHASES[engine], [round(v, 3) for v in pl["phase_ms"][:7]]))
+        roof["warp_ms_max_over_ctas"] = dict(zip(PHASES[engine], [round(v, 3) for v in pl["phase_ms_max"][:7]]))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {
-                "workload": args.workload, "n_obs": n, "K": K, "N": N, "particles": P, "rho": cfg["rho"],
-                "features": D, "observation_steps_per_sweep": steps_obs,
-                "chain_state": f"settled: {BURN_IN} untimed burn-in sweeps from the random initial allocation "
-                               "(the same protocol as the reference arm)",
-                "burn_in_kernel_ms": [round(v, 2) for v in burn_ms],
+            "config": common_config(cfg, BURN_IN),
+            "detail": {
+                "engine": engine,
                 "step": "one full conditional-SMC sweep (prefix build, per-observation loop, selection)",
+                "burn_in_kernel_ms": [round(v, 2) for v in burn_ms],
                 "parallelism": "single GPU" if world == 1 else
-                               f"one chain, {P} particles sharded over {world} GPUs ({P // world} per GPU): ESS partials, "
-                               "log-weights and allocations exchanged per observation with NVLink peer stores inside the "
-                               "sweep kernel, resampled ancestors pulled through peer memory; a host barrier between "
-                               "upload and run of every sweep",
+                               f"one chain, {P} particles sharded over {world} GPUs ({P // world} per GPU): every rank keeps its own "
+                               "copy-on-write pool; per observation one ESS partial per rank is pushed to the peers (NVLink stores, "
+                               "off the dependent chain), allocations go to every rank's log; resampled ancestors held by another "
+                               "rank have their rows pulled through peer memory; a host barrier between upload and run of every sweep",
                 "particles_per_gpu": P // world,
                 "rows_pulled_from_peers_per_sweep": remote_rows / args.steps,
-                "l2": "256 MiB buffer written between timed sweeps (L2 flush); per-particle statistics "
-                      f"{sum(P * N * D[k] * (32 if types[k] == 0 else 8) for k in range(K)) / 1e6:.0f} MB > 126 MB L2",
-                "empty_clusters": "labels with n == 0 share one evaluation per step (same result as evaluating "
-                                  "each; the reference evaluates unique clusters only)",
+                "distinct_clusters_evaluated_per_sweep": float(pl["rows"].sum()) / args.steps,
+                "row_evaluations_computed_per_sweep": float(pl["rows_computed"].sum()) / args.steps,
+                "occupied_particle_clusters_referenced_per_sweep": float(pl["rows_ref"].sum()) / args.steps,
                 "evals_performed_frac": evals / (dense * args.steps),
-                "resamples_per_sweep": resamples / args.steps, "copies_per_sweep": ncopies / args.steps,
+                "resamples_per_sweep": pl["resamples"] / args.steps,
             },
-            "mcmc_sweeps_per_s": world * args.steps / (dev_ms * 1e-3),
+            "mcmc_sweeps_per_s": args.steps / (dev_ms * 1e-3),
             "ms_per_timed_step": [round(v, 3) for v in step_ms],
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / args.steps,
                     "path": "pmdi_sweep() C-ABI call with host buffers, allocations chained sweep to sweep"},
-            "gpu_launches": 8 * args.steps,  # per sweep: sweep_init, prefix_lists, prefix_build, proto_aux, broadcast, empty_lp, k_sweep, finish
-            "roofline": {
-                "bound": "hbm", "kernel": "k_sweep (persistent, one launch per sweep)" +
-                                          ("" if world == 1 else "; rank 0's launch and rank 0's own particles"),
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": peak_src, "traffic": traffic,
-                "algorithmic_bytes_per_launch": alg, "kernel_ms": k_ms,
-                "achieved_stored_width": alg_stored / (k_ms * 1e-3) / 1e9,
-                "note": "algorithmic bytes = rows actually evaluated x D x (16|8|8 B) + P x D x (64|16|16 B) "
-                        "per observation step at the reference's f64/Int64 widths (SURVEY 8(d)); "
-                        "empty labels are not read",
-                "kernel_share_of_step": k_ms / (dev_ms / args.steps),
-                "warp_ms_mean_over_ctas": dict(zip(PHASES, phase_ms[:7])),
-                "warp_ms_max_over_ctas": dict(zip(PHASES, phase_ms_max[:7])),
-            },
+            "gpu_launches": LAUNCHES[engine] * args.steps,
+            "roofline": roof,
+            "parity": parity,
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_leg(cfg)
-        else:
-            line["cpu_baseline"] = None
+        if cfg4 is not None:
+            line["cfg4" if world == 1 else "cfg4_strong"] = cfg4
+        if pmdi_e2e is not None:
+            line["pmdi_end_to_end"] = pmdi_e2e
+        line["cpu_baseline"] = cpu_baseline_leg(cfg) if (world == 1 and not args.no_cpu) else None
         print(json.dumps(line), flush=True)
-    ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def cfg4_block(world, rank, local, stream, flush, peak, peak_src, traffic_for, steps=3, burn=3):
+    """configs[3]: 20,000 cells x 2,000 genes x 2, N=50, 1,024 particles - the configuration the north-star puts
+    its 60 %-of-HBM target on.  N = 1: the default engine, and the dense engine whose regime the HBM roofline
+    describes.  N > 1: the 1,024 particles sharded over the N GPUs (strong scaling)."""
+    cfg = make_workload("cfg4_singlecell")
+    rng = np.random.default_rng(4)
+    orders = [rng.permutation(cfg["n"]) + 1 for _ in range(burn + 2 * steps + 4)]
+    out = {"config": common_config(cfg, burn), "scaling": "strong" if world > 1 else None}
+    run = Runner(cfg, world, rank, local, stream, flush)
+    burn_ms = []
+    run.chain(burn, orders, burn_ms)
+    dev_ms, step_ms = run.timed(steps, orders)
+    pl = run.per_launch(steps, orders)
+    run.close()
+    k_ms = float(np.mean(pl["kms"]))
+    engine = pl["engine"]
+    out.update({"engine": engine, "ms_per_sweep": dev_ms / steps, "ms_per_timed_sweep": [round(v, 2) for v in step_ms],
+                "value": dense_evals_per_sweep(cfg) * steps / (dev_ms * 1e-3), "unit": UNIT,
+                "burn_in_kernel_ms": [round(v, 1) for v in burn_ms],
+                "distinct_clusters_evaluated_per_sweep": float(pl["rows"].sum()) / steps,
+                "particles_per_gpu": cfg["P"] // world,
+                "roofline": roofline(cfg, pl, steps, k_ms, world, peak, peak_src,
+                                     traffic_for("cfg4_singlecell", cfg["P"], engine), engine)})
+    if world == 1:
+        d = Runner(cfg, 1, 0, local, stream, flush, engine="dense")
+        d.s, d.it = run.s, run.it   # the same chain state
+        dsteps = 2
+        d.chain(1, orders)
+        ddev, dstep = d.timed(dsteps, orders)
+        dpl = d.per_launch(dsteps + 1, orders)
+        d.close()
+        dk = float(np.mean(dpl["kms"]))
+        roof = roofline(cfg, dpl, dsteps + 1, dk, 1, peak, peak_src, traffic_for("cfg4_singlecell", cfg["P"], "dense"), "dense")
+        if roof["traffic"]:
+            roof["frac_by_measured_dram_traffic"] = roof["traffic"] / (dk * 1e-3) / 1e9 / peak
+        out["dense_engine"] = {"ms_per_sweep": ddev / dsteps, "ms_per_timed_sweep": [round(v, 1) for v in dstep],
+                               "rows_evaluated_per_sweep": float(dpl["rows"].sum()) / (dsteps + 1), "roofline": roof,
+                               "note": "PMDI_ENGINE=dense: every particle owns its N clusters per dataset (the form the HBM "
+                                       "roofline describes); the default engine does the same sweep, same results, in "
+                                       f"{dev_ms / steps:.0f} ms"}
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["ms_per_sweep"] = float(t[0]) / steps
+        out["value"] = dense_evals_per_sweep(cfg) * steps / (float(t[0]) * 1e-3)
+    return out if rank == 0 else None
+
+
+def pmdi_block(local, iters=12):
+    """MCMC iterations per second through pmdi() - the sweep on the GPU plus the host-side hyper-parameter
+    updates, align_labels! and the CSV writer (src/pmdi.jl:164-384) - for the configurations whose N^K
+    hyper-parameter tables fit."""
+    from pmdi_b200 import pmdi as host
+    out = {}
+    for name in ("cfg1_iris", "cfg2_multiomics"):
+        cfg = make_workload(name)
+        with tempfile.TemporaryDirectory() as td:
+            t0 = time.perf_counter()
+            st = host.pmdi(cfg["data"], cfg["types"], cfg["N"], cfg["P"], cfg["rho"], iters, os.path.join(td, "out.csv"),
+                           seed=1, device=local)
+            dt = time.perf_counter() - t0
+        out[name] = {"iterations": iters, "mcmc_iters_per_s": iters / dt, "ms_per_iteration": 1e3 * dt / iters,
+                     "sweep_device_ms_per_iteration": st["sweep_device_ms"] / iters,
+                     "note": "first iterations of a fresh chain (the expensive regime), context creation and data upload included"}
+    return out
 
 
 def main():
@@ -419,6 +619,9 @@ def main():
     ap.add_argument("--workload", default="cfg2_multiomics")
     ap.add_argument("--particles", type=int, default=None)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-cfg4", action="store_true", help="skip the cfg4 block")
+    ap.add_argument("--no-pmdi", action="store_true", help="skip the pmdi() end-to-end block")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity check against the oracle")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

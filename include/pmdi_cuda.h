@@ -146,6 +146,9 @@ typedef struct pmdi_sweep_out {
   int64_t  rows_computed[8]; /* per dataset: row evaluations the device performed.  Engine 2 evaluates every
                              live row AND its child (the row plus the previous observation) one step ahead,
                              so this is about twice rows_evaluated; engines 0/1: equal to rows_evaluated  */
+  int64_t  rows_added[8]; /* per dataset: clusters that had an observation added (the reference's cluster_add!
+                             calls, src/pmdi.jl:275-310: one per DISTINCT chosen cluster and step; dense: one per
+                             particle and step)                                                    */
 } pmdi_sweep_out;
 
 /*

@@ -64,7 +64,7 @@ class SweepOut(C.Structure):
         ("dbg_anc", C.c_void_p), ("cluster_n", C.c_void_p),
         ("label_counts", C.c_void_p), ("pair_agree", C.c_void_p),
         ("rows_referenced", C.c_int64 * 8), ("engine", C.c_int32), ("rows_evaluated_ahead", C.c_int64),
-        ("rows_computed", C.c_int64 * 8),
+        ("rows_computed", C.c_int64 * 8), ("rows_added", C.c_int64 * 8),
     ]
 
 
@@ -286,6 +286,7 @@ class Context:
         res["rows_referenced"] = [int(v) for v in o.rows_referenced]
         res["engine"] = {0: "dense", 1: "pool", 2: "spec"}[int(o.engine)]
         res["rows_computed"] = [int(v) for v in o.rows_computed]
+        res["rows_added"] = [int(v) for v in o.rows_added]
         res["rows_evaluated_ahead"] = int(o.rows_evaluated_ahead)
         res["device_ms"] = float(o.device_ms)
         res["sweep_kernel_ms"] = float(o.sweep_kernel_ms)

@@ -139,7 +139,7 @@ struct pmdi_ctx {
   DevBuf<unsigned char> dec;
   DevBuf<int4> glist, elist;
   DevBuf<int> gcnt;
-  DevBuf<unsigned long long> rows_spec;
+  DevBuf<unsigned long long> rows_spec, rows_add;
   DevBuf<double> dbg_lp, dbg_lw, scratch_d;
   DevBuf<int> dbg_alloc, dbg_anc, scratch_i, wd_state;
   DevBuf<uint8_t> scratch_u8;
@@ -548,7 +548,7 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   for (auto* b : dl) b->release();
   c->lab.release(); c->alloc_log.release(); c->copies.release(); c->bar.release();
   c->rows_eval.release(); c->phase_ns.release(); c->scratch_u8.release();
-  c->dec.release(); c->rows_spec.release(); c->glist.release(); c->elist.release(); c->gcnt.release();
+  c->dec.release(); c->rows_spec.release(); c->rows_add.release(); c->glist.release(); c->elist.release(); c->gcnt.release();
   c->rows_ref.release(); c->trace.release(); c->wd_state.release(); c->pull_jobs.release(); c->rank_part.release();
   c->label_counts.release(); c->pair_agree.release();
   for (int r = 0; r < c->R; ++r)
@@ -778,9 +778,10 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   CK(c->cur_at.ensure(steps));
   CK(c->rows_ref.ensure(PMDI_MAX_K)); CK(c->label_counts.ensure((size_t)N * K)); CK(c->pair_agree.ensure(std::max(npairs, 1)));
   sp.rows_ref = c->rows_ref.p;
-  CK(c->dec.ensure(steps)); CK(c->rows_spec.ensure(PMDI_MAX_K));
+  CK(c->dec.ensure(steps)); CK(c->rows_spec.ensure(PMDI_MAX_K)); CK(c->rows_add.ensure(PMDI_MAX_K));
   CK(cudaMemsetAsync(c->rows_spec.p, 0, 8 * PMDI_MAX_K, st));
-  sp.dec = c->dec.p; sp.rows_spec = c->rows_spec.p;
+  CK(cudaMemsetAsync(c->rows_add.p, 0, 8 * PMDI_MAX_K, st));
+  sp.dec = c->dec.p; sp.rows_spec = c->rows_spec.p; sp.rows_add = c->rows_add.p;
   if (c->engine == 2) {  // the live-row list: at most one entry per (particle slot, label) and dataset
     const long long lcap = (long long)K * ((long long)c->Ps * N + N + 2);
     CK(c->glist.ensure(lcap)); CK(c->gcnt.ensure(4));
@@ -899,7 +900,7 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   const int steps = c->sp.steps;
   int err = 0;
   long long counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  unsigned long long rows[PMDI_MAX_K], rref[PMDI_MAX_K], rspec[PMDI_MAX_K];
+  unsigned long long rows[PMDI_MAX_K], rref[PMDI_MAX_K], rspec[PMDI_MAX_K], radd[PMDI_MAX_K];
   std::vector<unsigned long long> phase(8 * (size_t)c->G, 0ull);
   long long pstar = 0;
   CK(cudaMemcpyAsync(&err, c->err.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -907,6 +908,7 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
   CK(cudaMemcpyAsync(rows, c->rows_eval.p, sizeof(rows), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(rref, c->rows_ref.p, sizeof(rref), cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(rspec, c->rows_spec.p, sizeof(rspec), cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(radd, c->rows_add.p, sizeof(radd), cudaMemcpyDeviceToHost, st));
   if (o->label_counts)
     CK(cudaMemcpyAsync(o->label_counts, c->label_counts.p, sizeof(int64_t) * N * K, cudaMemcpyDeviceToHost, st));
   if (o->pair_agree && K > 1)
@@ -969,8 +971,9 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
     o->rows_evaluated[k] = (int64_t)rows[k];
     o->rows_referenced[k] = (int64_t)rref[k];
     o->rows_computed[k] = c->engine == 2 ? (int64_t)rspec[k] : (int64_t)rows[k];
+    o->rows_added[k] = c->engine ? (int64_t)radd[k] : (int64_t)steps * c->Ps;  // dense: every particle's chosen cluster
   }
-  for (int k = K; k < 8; ++k) { o->rows_evaluated[k] = 0; o->rows_referenced[k] = 0; o->rows_computed[k] = 0; }
+  for (int k = K; k < 8; ++k) { o->rows_evaluated[k] = 0; o->rows_referenced[k] = 0; o->rows_computed[k] = 0; o->rows_added[k] = 0; }
   o->engine = c->engine;
   o->n_evals = ev;
   o->n_evals_dense = dense;

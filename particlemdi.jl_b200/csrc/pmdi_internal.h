@@ -95,6 +95,8 @@ struct __attribute__((aligned(16))) SweepParams {
   long long lcap;
   int fc_target;          /* spec engine: free-row ids an E-CTA keeps cached per dataset        */
   int pad1;
+  unsigned long long* rows_add;  /* [K] clusters that had an observation added (pool / spec engines) */
+  unsigned long long* pad2;
   int obs_ring;           /* depth of the shared-memory observation ring (2..4)              */
   long long proto_base;   /* first row of the rho-prefix prototypes (dense: Ps*N, pool: 0)   */
   unsigned long long wd_ns; /* watchdog of the in-kernel waits                               */

@@ -56,7 +56,7 @@ struct PoolSmem {
   int pdone;                   // particles of this CTA folded this step
   int U[2][PMDI_MAX_K];        // by step parity: live rows of each dataset covered by the E phase
   int rbase[2][PMDI_MAX_K + 1];  // by step parity: first row task of each dataset
-  unsigned rows_eval[PMDI_MAX_K], rows_ref[PMDI_MAX_K];
+  unsigned rows_eval[PMDI_MAX_K], rows_ref[PMDI_MAX_K], rows_add[PMDI_MAX_K];
   unsigned long long tacc[8];
   int tr_n[POOL_NW];
 };
@@ -276,6 +276,7 @@ __device__ __noinline__ void pool_eval_rows(const SweepParams& sp, PoolSmem& sm,
         __stcg(sp.pd[k].lp + c, vs);
       }
       atomicAdd(&sm.rows_eval[k], mode == 2 ? 2u : 1u);
+      if (mode) atomicAdd(&sm.rows_add[k], 1u);
     }
   }
 }
@@ -845,7 +846,7 @@ __device__ __forceinline__ void pool_sweep_body(const SweepParams& sp, PoolSmem&
   for (int sl = tid; sl < ns; sl += PMDI_NT) { T.lw_s[sl] = sp.lw_init; T.pcount[sl] = 0; }
 #pragma unroll 1
   for (int u = tid; u < nu; u += PMDI_NT) { T.u_duty[u] = 0; T.u_ks[u] = (u % K) | ((u / K) << 8); }
-  if (tid < PMDI_MAX_K) { sm.rows_eval[tid] = 0; sm.rows_ref[tid] = 0; }
+  if (tid < PMDI_MAX_K) { sm.rows_eval[tid] = 0; sm.rows_ref[tid] = 0; sm.rows_add[tid] = 0; }
   if (tid < 8) sm.tacc[tid] = 0;
   if (tid < POOL_NW) sm.tr_n[tid] = 0;
   if (tid == 0) {
@@ -936,6 +937,7 @@ __device__ __forceinline__ void pool_sweep_body(const SweepParams& sp, PoolSmem&
   if (tid < K) {
     atomicAdd(sp.rows_eval + tid, (unsigned long long)sm.rows_eval[tid]);
     atomicAdd(sp.rows_ref + tid, (unsigned long long)sm.rows_ref[tid]);
+    atomicAdd(sp.rows_add + tid, (unsigned long long)sm.rows_add[tid]);
   }
   if (cta == 0)  // after a final resampling all log-weights are 1.0 (src/pmdi.jl:319)
 #pragma unroll 1

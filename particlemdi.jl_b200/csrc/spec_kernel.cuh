@@ -55,6 +55,7 @@ struct SpecSmem {
   int wsum[POOL_NW];           // E-CTA: per-warp survivor counts of the running fix
   int b_tt[PMDI_MAX_K], b_c[PMDI_MAX_K], b_cc[PMDI_MAX_K], b_next[PMDI_MAX_K];  // E-CTA: the empty clusters' children
   int kc[PMDI_MAX_K];          // E-CTA 0: entries per dataset
+  unsigned kadd[PMDI_MAX_K];   // E-CTA 0: clusters that were chosen (the reference's cluster_add! calls)
   unsigned rows_eval[PMDI_MAX_K], rows_ref[PMDI_MAX_K], rows_spec[PMDI_MAX_K];
   unsigned long long tacc[8];
   int tr_n[POOL_NW];
@@ -493,7 +494,7 @@ __device__ __noinline__ void spec_fix(const SweepParams& sp, SpecSmem& sm, const
       const int cc = ldcg_info(pd.info + (size_t)parn * pd.cap + c).z;
       const bool own = (i % GE) == e;
       const int kc = (k << SPEC_KSHIFT) | c;
-      if (e == 0) atomicAdd(&sm.kc[k], (tot == 0 || tot == rf) ? 1 : 2);
+      if (e == 0) { atomicAdd(&sm.kc[k], (tot == 0 || tot == rf) ? 1 : 2); if (tot) atomicAdd(&sm.kadd[k], 1u); }
       if (tot == 0) {  // nobody chose v
         ns = 1; s0 = make_int4(en.x, cv, n, 0);
         if (own) { __stcg(pd.refcnt + (size_t)parn * pd.cap + v, rf); spec_free_id(sp, T, k, c); spec_free_id(sp, T, k, cc); }
@@ -538,7 +539,7 @@ __device__ __noinline__ void spec_fix(const SweepParams& sp, SpecSmem& sm, const
     if (tt > 0) {
       if (tid == 0) spec_set_entry(sp, T, e, ln, nb, make_int4((k << SPEC_KSHIFT) | c, cc, 1, 0));
       if (own) __stcg(sp.pd[k].refcnt + (size_t)parn * sp.pd[k].cap + c, tt);
-      if (e == 0 && tid == 0) sm.kc[k] += 1;
+      if (e == 0 && tid == 0) { sm.kc[k] += 1; sm.kadd[k] += 1u; }
       ++nb;
     } else if (own) {
       spec_free_id(sp, T, k, c); spec_free_id(sp, T, k, cc);
@@ -799,7 +800,7 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
   T.el_s = (int4*)rt;  // the two roles overlay the same region
   T.fc_s = (int*)(T.el_s + (size_t)2 * SPEC_EC);
   T.fc_top = T.fc_s + (size_t)K * SPEC_FC;
-  if (tid < PMDI_MAX_K) { sm.rows_eval[tid] = 0; sm.rows_ref[tid] = 0; sm.rows_spec[tid] = 0; }
+  if (tid < PMDI_MAX_K) { sm.rows_eval[tid] = 0; sm.rows_ref[tid] = 0; sm.rows_spec[tid] = 0; sm.kadd[tid] = 0; }
   if (tid < 8) sm.tacc[tid] = 0;
   if (tid < POOL_NW) sm.tr_n[tid] = 0;
   if (tid == 0) {
@@ -911,6 +912,7 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
     atomicAdd(sp.rows_eval + tid, (unsigned long long)sm.rows_eval[tid]);
     atomicAdd(sp.rows_ref + tid, (unsigned long long)sm.rows_ref[tid]);
     atomicAdd(sp.rows_spec + tid, (unsigned long long)sm.rows_spec[tid]);
+    atomicAdd(sp.rows_add + tid, (unsigned long long)sm.kadd[tid]);
   }
   if (cta == 0)  // after a final resampling all log-weights are 1.0 (src/pmdi.jl:319)
     for (int p = tid; p < sp.P; p += PMDI_NT)
