@@ -257,7 +257,7 @@ class Runner:
     def _sync_ranks(self):
         """With several ranks every rank's grid counter must be reset (upload) before any rank's
         kernel starts to arrive on it (include/pmdi_cuda.h)."""
-        if self.world > 1:
+        if self.world > 1 and os.environ.get("PMDI_ENGINE") == "dense":
             self.dist.barrier()
 
     def chain(self, sweeps, orders, record=None):

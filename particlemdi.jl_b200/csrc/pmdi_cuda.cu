@@ -145,6 +145,9 @@ struct pmdi_ctx {
   DevBuf<uint8_t> scratch_u8;
   SweepParams sp;
   bool uploaded = false, ran = false;
+  unsigned long long sweep_seq = 1;  // pool / spec engines: counters and step tags run on from sweep to sweep
+  DevBuf<unsigned long long> bar_state;
+  bool bar_state_init = false;
   unsigned sweep_flags = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev2 = nullptr, ev3 = nullptr;
 };
@@ -233,10 +236,10 @@ int build_layout(pmdi_ctx* c) {
   const char* eng = getenv("PMDI_ENGINE");
   // (spec deals one row task per evaluation CTA and step: with many datasets a step has more tasks than
   // evaluation CTAs and the two-barrier form, which uses every SM for the evaluations, measured faster - cfg3)
-  c->engine = (c->R > 1 || c->K > 4) ? 1 : 2;
+  c->engine = c->K > 4 ? 1 : 2;
   if (eng && std::string(eng) == "dense") c->engine = 0;
   if (eng && std::string(eng) == "pool") c->engine = 1;
-  if (eng && std::string(eng) == "spec" && c->R == 1) c->engine = 2;
+  if (eng && std::string(eng) == "spec") c->engine = 2;
   // spec engine: role split of the grid (proposal CTAs own particle slots, evaluation CTAs own rows)
   {
     // proposal CTAs: one (dataset, particle) unit per warp where the SMs allow it; the rest evaluate rows
@@ -279,7 +282,7 @@ int build_layout(pmdi_ctx* c) {
   // chosen row in flight (<= Ps per dataset), the N prefix rows, the empty cluster; with several ranks a
   // resampling pulls the rows of remote ancestors before the dead local rows are freed (another Ps*N at most)
   // spec: a live row holds its child and the two ids handed out for the next step (x4)
-  const long long rows = c->engine == 2 ? 4ll * c->Ps * c->N + c->N + 4096
+  const long long rows = c->engine == 2 ? (c->R > 1 ? 8ll : 4ll) * c->Ps * c->N + c->N + 4096
                        : c->engine ? (long long)(c->R > 1 ? 2 : 1) * c->Ps * c->N + c->Ps + c->N + 2
                                    : (long long)(c->Ps + 2) * c->N;
   if (rows > 0x7fffff00ll) return fail(1, "pmdi: particles x N too large");
@@ -289,7 +292,7 @@ int build_layout(pmdi_ctx* c) {
   const size_t o_bar = take(64);
   const size_t o_ess = take(sizeof(double) * 6 * (size_t)c->R * Gmax);
   const size_t o_lw = take(sizeof(double) * (size_t)c->P);
-  const size_t o_log = take((size_t)c->n * K * c->P);  // at most n_obs observation steps
+  const size_t o_log = take(2 * (size_t)c->n * K * c->P);  // at most n_obs observation steps; two sweeps' worth (below)
   const size_t o_rankp = take(sizeof(double) * 2 * 8 * 4);
   struct Off { size_t mu, lamn, sum, beta, cnt, S, part, aux, n, cw, refcnt, chosen, dst, neval, live, free_, rowmap, ctr, lp, info, mark; };
   std::vector<Off> offs(K);
@@ -330,7 +333,7 @@ int build_layout(pmdi_ctx* c) {
   c->bar.view(A + o_bar, 16);
   c->ess_part.view(A + o_ess, 6 * (size_t)c->R * Gmax);
   c->lw.view(A + o_lw, c->P);
-  c->alloc_log.view(A + o_log, (size_t)c->n * K * c->P);
+  c->alloc_log.view(A + o_log, 2 * (size_t)c->n * K * c->P);
   c->rank_part.view(A + o_rankp, 2 * 8 * 4);
   for (int k = 0; k < K; ++k) {
     Dataset& s = c->ds[k];
@@ -548,7 +551,7 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   for (auto* b : dl) b->release();
   c->lab.release(); c->alloc_log.release(); c->copies.release(); c->bar.release();
   c->rows_eval.release(); c->phase_ns.release(); c->scratch_u8.release();
-  c->dec.release(); c->rows_spec.release(); c->rows_add.release(); c->glist.release(); c->elist.release(); c->gcnt.release();
+  c->dec.release(); c->rows_spec.release(); c->rows_add.release(); c->bar_state.release(); c->glist.release(); c->elist.release(); c->gcnt.release();
   c->rows_ref.release(); c->trace.release(); c->wd_state.release(); c->pull_jobs.release(); c->rank_part.release();
   c->label_counts.release(); c->pair_agree.release();
   for (int r = 0; r < c->R; ++r)
@@ -794,14 +797,20 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   }
   sp.pull_jobs = nullptr;
   if (c->engine && c->R > 1) {
-    CK(c->pull_jobs.ensure((size_t)K * c->Ps * N));
+    CK(c->pull_jobs.ensure(2 * (size_t)K * c->Ps * N));
     sp.pull_jobs = c->pull_jobs.p;
   }
   sp.n1 = (int)a->n1; sp.steps = steps; sp.flags = (int)a->flags;
   sp.Pi = c->Pi.p; sp.l1phi = c->l1phi.p; sp.s_in = c->s_in.p; sp.order = c->order.p;
   sp.lw_init = a->logweight_init; sp.seed = a->seed; sp.iter = a->iter;
   sp.lw = c->lw.p; sp.ess_part = c->ess_part.p; sp.lw_out = c->lw_out.p; sp.slot_of = c->slot_of.p; sp.logical_of = c->logical_of.p;
-  sp.inc = c->inc.p; sp.lp_empty = c->lp_empty.p; sp.lab = c->lab.p; sp.alloc_log = c->alloc_log.p;
+  sp.inc = c->inc.p; sp.lp_empty = c->lp_empty.p; sp.lab = c->lab.p;
+  // a peer that is one sweep ahead writes its allocations into the other half while this rank's finish kernel reads
+  sp.alloc_log = c->alloc_log.p + (c->sweep_seq & 1) * (size_t)n * K * P;
+  sp.tag_base = c->sweep_seq << 32;
+  CK(c->bar_state.ensure(2));
+  if (!c->bar_state_init) { CK(cudaMemsetAsync(c->bar_state.p, 0, 16, st)); c->bar_state_init = true; }
+  sp.bar_state = c->bar_state.p;
   sp.anc_log = c->anc_log.p; sp.ev_of_step = c->ev_of_step.p;
   sp.sc_w = c->sc_w.p; sp.sc_pp = c->sc_pp.p; sp.sc_u = c->sc_u.p; sp.sc_j = c->sc_j.p;
   sp.sc_anc0 = c->sc_anc0.p; sp.sc_a = c->sc_a.p; sp.sc_b = c->sc_b.p; sp.sc_c = c->sc_c.p;
@@ -821,8 +830,9 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   }
   if (c->R > 1 && c->peer_base[c->rank] == nullptr)
     return fail(1, "pmdi_sweep: call pmdi_ipc_export / pmdi_ipc_import on every rank first");
-  CK(cudaMemsetAsync(c->bar.p, 0, 16, st));  // with R > 1 the caller barriers all ranks between upload and run
-  CK(cudaMemsetAsync(c->rank_part.p, 0, sizeof(double) * 2 * 8 * 4, st));  // the step tags of the previous sweep
+  if (!c->engine) {  // dense engine: counters restart; with R > 1 the caller barriers all ranks between upload and run
+    CK(cudaMemsetAsync(c->bar.p, 0, 16, st));
+  }
   CK(cudaMemsetAsync(c->phase_ns.p, 0, 64 * (size_t)c->G, st));
   CK(c->wd_state.ensure((size_t)c->G * 16 * 16));
   CK(cudaMemsetAsync(c->wd_state.p, 0xff, sizeof(int) * (size_t)c->G * 16 * 16, st));
@@ -887,6 +897,7 @@ int pmdi_sweep_run(pmdi_ctx* c) {
                                    c->cluster_n.p, c->cur_at.p, c->label_counts.p, c->pair_agree.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev3, st));
+  c->sweep_seq += 1;
   c->ran = true;
   return 0;
 }

@@ -96,7 +96,10 @@ struct __attribute__((aligned(16))) SweepParams {
   int fc_target;          /* spec engine: free-row ids an E-CTA keeps cached per dataset        */
   int pad1;
   unsigned long long* rows_add;  /* [K] clusters that had an observation added (pool / spec engines) */
-  unsigned long long* pad2;
+  /* pool / spec engines: the barrier counters and the step tags of the rank partials run on from sweep to
+     sweep (nothing a peer can reach is reset between sweeps, so the ranks need no host barrier) */
+  unsigned long long tag_base;
+  unsigned long long* bar_state;  /* [2] where the local / cross-rank counters stand; written at the end of a sweep */
   int obs_ring;           /* depth of the shared-memory observation ring (2..4)              */
   long long proto_base;   /* first row of the rho-prefix prototypes (dense: Ps*N, pool: 0)   */
   unsigned long long wd_ns; /* watchdog of the in-kernel waits                               */

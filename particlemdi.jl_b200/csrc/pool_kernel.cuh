@@ -47,6 +47,7 @@ struct PoolSmem {
   unsigned long long obs_bar[PMDI_OBS_RING];
   unsigned long long epoch;    // local grid-barrier arrivals expected so far
   unsigned long long xepoch;   // cross-rank barrier arrivals expected so far (one per rank)
+  unsigned long long flag_base;  // resampling decisions attached to the counter before this sweep
   double res_mx;
   double red[2][2][32];        // [row-iteration parity][updated or plain / split source][block] partials
   int res_flag;                // the last resolved step resamples
@@ -118,7 +119,7 @@ __device__ __noinline__ bool pool_gsync(const SweepParams& sp, PoolSmem& sm, int
         }
       }
     }
-    if (b1) sm.res_flag = (((v >> POOL_FLAG_SHIFT) - (unsigned long long)sm.ev) & 0xFFFFFull) != 0ull;
+    if (b1) sm.res_flag = (((v >> POOL_FLAG_SHIFT) - sm.flag_base - (unsigned long long)sm.ev) & 0xFFFFFull) != 0ull;
   }
   __syncthreads();
   return sm.fail == 0;
@@ -776,7 +777,7 @@ __device__ __forceinline__ void pool_push_rank_partial(const SweepParams& sp, in
 #pragma unroll 1
     for (int r = 0; r < sp.R; ++r) {
       unsigned long long* f = (unsigned long long*)(on_rank(sp, mine, r) + 3);
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"((unsigned long long)(t + 1)) : "memory");
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sp.tag_base + (unsigned long long)(t + 1)) : "memory");
     }
   }
 }
@@ -789,7 +790,7 @@ __device__ __noinline__ void pool_resolve_ranks(const SweepParams& sp, PoolSmem&
     const unsigned long long t0 = globaltimer_ns();
     unsigned spins = 0;
 #pragma unroll 1
-    while (ld_acquire_sys_u64(f) < (unsigned long long)(t + 1)) {
+    while (ld_acquire_sys_u64(f) < sp.tag_base + (unsigned long long)(t + 1)) {
       if (((++spins) & 0x3ffu) == 0) {
         if (__ldcg(sp.err) != 0) break;
         if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); break; }
@@ -850,7 +851,9 @@ __device__ __forceinline__ void pool_sweep_body(const SweepParams& sp, PoolSmem&
   if (tid < 8) sm.tacc[tid] = 0;
   if (tid < POOL_NW) sm.tr_n[tid] = 0;
   if (tid == 0) {
-    sm.res_flag = 0; sm.res_next = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.epoch = 0; sm.xepoch = 0; sm.res_mx = 0.0;
+    sm.res_flag = 0; sm.res_next = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.res_mx = 0.0;
+    const unsigned long long b0 = __ldcg(sp.bar_state);  // the counters run on from the previous sweep
+    sm.epoch = b0 & POOL_ARRIVE_MASK; sm.flag_base = b0 >> POOL_FLAG_SHIFT; sm.xepoch = __ldcg(sp.bar_state + 1);
 #pragma unroll 1
     for (int b = 0; b < sp.obs_ring; ++b) mbar_init(&sm.obs_bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -947,6 +950,10 @@ __device__ __forceinline__ void pool_sweep_body(const SweepParams& sp, PoolSmem&
   if (cta == 0 && tid == 0) sp.counters[2] = sm.ev;
   // the peers' stores into this rank's allocation log have landed before the finish kernel reads it
   if (sp.R > 1) pool_xsync(sp, sm);
+  if (cta == 0 && tid == 0) {  // where the next sweep's counters start
+    sp.bar_state[0] = ((sm.flag_base + (unsigned long long)sm.ev) << POOL_FLAG_SHIFT) + sm.epoch;
+    sp.bar_state[1] = sm.xepoch;
+  }
 #undef PHASE_MARK
 }
 

@@ -118,6 +118,32 @@ __device__ __noinline__ bool spec_gsync(const SweepParams& sp, SpecSmem& sm, boo
   return sm.fail == 0;
 }
 
+// barrier over the CTAs of ALL ranks: local barrier (peer stores made visible system-wide), one arrival per
+// rank on every rank's counter (NVLink peer atomics), local barrier.  Resampling and the end of the sweep.
+__device__ __noinline__ bool spec_xsync(const SweepParams& sp, SpecSmem& sm) {
+  if (!spec_gsync(sp, sm, sp.R > 1)) return false;
+  if (sp.R > 1) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long* xbar = (unsigned long long*)sp.bar + 1;
+      sm.xepoch += (unsigned long long)sp.R;
+      __threadfence_system();
+#pragma unroll 1
+      for (int r = 0; r < sp.R; ++r) atomicAdd_system(on_rank(sp, xbar, r), 1ull);
+      const unsigned long long t0 = globaltimer_ns();
+      unsigned spins = 0;
+      while (ld_acquire_sys_u64(xbar) < sm.xepoch) {
+        if (((++spins) & 0x3ffu) == 0) {
+          if (__ldcg(sp.err) != 0) break;
+          if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); break; }
+        }
+      }
+      __threadfence_system();
+    }
+    if (!spec_gsync(sp, sm)) return false;
+  }
+  return true;
+}
+
 __device__ __forceinline__ int4 ldcg_info(const RowInfo* p) { return __ldcg((const int4*)p); }
 __device__ __forceinline__ double info_lp(const int4& v) { return __hiloint2double(v.y, v.x); }
 
@@ -270,7 +296,8 @@ __device__ __noinline__ void spec_commit(const SweepParams& sp, SpecSmem& sm, co
 // when they need it - the proposals only at their commit, the evaluation CTAs before the barrier.
 __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, int t) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, P = sp.P;
-  const int per = (P + POOL_NW - 1) / POOL_NW, p_lo = warp * per, p_hi = min(P, p_lo + per);
+  // (with several ranks: this rank's particles; the ranks' partials are exchanged below)
+  const int per = (sp.Ps + POOL_NW - 1) / POOL_NW, p_lo = sp.slot0 + warp * per, p_hi = min(sp.slot0 + sp.Ps, p_lo + per);
   double mxv = -INFINITY;
 #pragma unroll 1
   for (int p0 = p_lo; p0 < p_hi; p0 += 256) {
@@ -308,7 +335,7 @@ __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, in
   __syncthreads();
   if (warp == 0) {
     const double m = lane < POOL_NW ? sm.red[0][0][lane] : -INFINITY;
-    const double mx = warp_max(m);
+    double mx = warp_max(m);
     double a = 0.0, b = 0.0;
     if (lane < POOL_NW && m > -INFINITY) {
       const double e = pm_exp(m - mx);
@@ -317,8 +344,47 @@ __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, in
     }
     a = warp_sum(a);
     b = warp_sum(b);
+    double gmx = mx;
+    if (sp.R > 1) {  // one (max, sum w, sum w^2) per rank, pushed to every rank with the step as its tag
+      const int par = t & 1;
+      double* mine = sp.rank_part + ((size_t)par * sp.R + sp.rank) * 4;
+      if (lane == 0) {
+#pragma unroll 1
+        for (int r = 0; r < sp.R; ++r) {
+          double* q = on_rank(sp, mine, r);
+          __stcg(q, mx); __stcg(q + 1, a); __stcg(q + 2, b);
+        }
+        // (the release store orders this thread's stores above before the tag: no separate system fence)
+#pragma unroll 1
+        for (int r = 0; r < sp.R; ++r) {
+          unsigned long long* f = (unsigned long long*)(on_rank(sp, mine, r) + 3);
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sp.tag_base + (unsigned long long)(t + 1)) : "memory");
+        }
+      }
+      const double* base = sp.rank_part + (size_t)par * sp.R * 4;
+      if (lane < sp.R) {
+        const unsigned long long* f = (const unsigned long long*)(base + (size_t)lane * 4 + 3);
+        const unsigned long long t0 = globaltimer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys_u64(f) < sp.tag_base + (unsigned long long)(t + 1)) {
+          if (((++spins) & 0x3ffu) == 0 && (__ldcg(sp.err) != 0 || globaltimer_ns() - t0 > sp.wd_ns)) { atomicExch(sp.err, 77); break; }
+        }
+      }
+      __syncwarp();
+      const double rm = lane < sp.R ? ldcg_f64(base + (size_t)lane * 4) : -INFINITY;
+      gmx = warp_max(rm);
+      double ra = 0.0, rb = 0.0;
+      if (lane < sp.R && rm > -INFINITY) {
+        const double e = pm_exp(rm - gmx);
+        ra = ldcg_f64(base + (size_t)lane * 4 + 1) * e;
+        rb = ldcg_f64(base + (size_t)lane * 4 + 2) * (e * e);
+      }
+      a = warp_sum(ra);
+      b = warp_sum(rb);
+    }
     if (lane == 0) {
       const int res = (a * a) / b <= 0.5 * (double)P ? 1 : 0;
+      mx = gmx;
       sm.res_mx = mx;
       sm.res_flag = res;
       if (!res) sp.ev_of_step[t] = -1;
@@ -649,6 +715,58 @@ __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, cons
   __syncthreads();
 }
 
+// One warp copies a live row of another rank's pool and that row's child of the coming step into local rows
+// (statistics, aux, cluster sizes, the predictives already computed for the next two observations) and
+// points their child links at the local ids handed to it.
+__device__ __noinline__ void spec_row_pull(const SweepParams& sp, int4 j0, int4 j1, int parn) {
+  const int k = j0.x & 0xff, ra = j0.x >> 8, rb = j0.y, v2 = j0.z, c2 = j0.w, a2 = j1.x, b2 = j1.y;
+  const DsDev& ds = sp.ds[k];
+  const PoolDev& pd = sp.pd[k];
+  const long long sdelta = sp.peer_delta[ra];
+  const int lane = threadIdx.x & 31, Dp = ds.Dp;
+#define PMDI_SRC(ptr_) ((decltype(ptr_))((const char*)(ptr_) + sdelta))
+  const RowInfo* rinfo = PMDI_SRC(pd.info);
+  const int4 i1 = ldcg_info(rinfo + (size_t)parn * pd.cap + rb);           // step st+1: lp, child
+  const int rc = i1.z;
+  const int4 i2 = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rb);     // step st+2: lp of the row
+  const int4 i2c = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rc);    //            lp of its child
+  const int n = ldcg_i32(PMDI_SRC(ds.n) + rb);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const long long src = h ? rc : rb, dst = h ? c2 : v2;
+    if (ds.type == T_GAUSSIAN) {
+#pragma unroll 1
+      for (int q = 2 * lane; q < Dp; q += 64) {
+        const double2 a = ldcg_f64x2(PMDI_SRC(ds.mu) + src * Dp + q), b = ldcg_f64x2(PMDI_SRC(ds.lamn) + src * Dp + q);
+        const double2 c = ldcg_f64x2(PMDI_SRC(ds.sum) + src * Dp + q), d = ldcg_f64x2(PMDI_SRC(ds.beta) + src * Dp + q);
+        *(double2*)(ds.mu + dst * Dp + q) = a; *(double2*)(ds.lamn + dst * Dp + q) = b;
+        *(double2*)(ds.sum + dst * Dp + q) = c; *(double2*)(ds.beta + dst * Dp + q) = d;
+      }
+    } else if (ds.type == T_CATEGORICAL) {
+      const long long W = (long long)Dp * pd.wpf;
+#pragma unroll 1
+      for (long long q = 2 * lane; q < W; q += 64)
+        *(ulonglong2*)(pd.cw + dst * W + q) = ldcg_u64x2(PMDI_SRC(pd.cw) + src * W + q);
+    } else {
+#pragma unroll 1
+      for (int q = 2 * lane; q < Dp; q += 64)
+        *(longlong2*)(ds.S + dst * Dp + q) = ldcg_i64x2(PMDI_SRC(ds.S) + src * Dp + q);
+    }
+#pragma unroll 1
+    for (int jj = lane; jj < ds.J; jj += 32) ds.aux[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + jj);
+  }
+#undef PMDI_SRC
+  if (lane == 0) {
+    ds.n[v2] = n; ds.n[c2] = n + 1; ds.n[a2] = n + 1; ds.n[b2] = n + 2;
+    int4 w = i1; w.z = c2; w.w = 0;
+    *(int4*)(pd.info + (size_t)parn * pd.cap + v2) = w;
+    w = i2; w.z = a2; w.w = 0;
+    *(int4*)(pd.info + (size_t)(parn ^ 1) * pd.cap + v2) = w;
+    w = i2c; w.z = b2; w.w = 0;
+    *(int4*)(pd.info + (size_t)(parn ^ 1) * pd.cap + c2) = w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Resampling after step `st` (src/pmdi.jl:318-341), all CTAs: every particle takes its ancestor's
 // row map; references are recounted; rows nobody refers to any more (and that are nobody's current
@@ -664,7 +782,8 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
   const int parn = (st + 1) & 1;  // info of step st+1: lp and child ids of everything that may be live;
                                   // also the copy of the reference counts the fix of step st+1 will read
   const bool has_next = st + 1 < sp.steps;
-  if (!spec_gsync(sp, sm)) return false;  // every E-CTA has finished E'(st+2), every commit of step st is in
+  // every E-CTA (of every rank) has finished E'(st+2), every commit of step st is in
+  if (!spec_xsync(sp, sm)) return false;
   if ((int)blockIdx.x == sp.G - 1) pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp);  // the D-CTA knows the maximum
   if (!spec_gsync(sp, sm)) return false;
   const int* anc = sp.anc_log + (size_t)ev * sp.P;
@@ -678,9 +797,58 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
 #pragma unroll 1
     for (long long i = gt; i < (long long)Ps * N; i += GT) {
       const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
-      const int a = ldcg_i32(anc + sp.slot0 + slot) - 1 - sp.slot0;
-      __stcg(rm_new + i, ldcg_i32(rm_old + (size_t)a * N + m));
+      const int a = ldcg_i32(anc + sp.slot0 + slot) - 1;
+      const int ra = a / Ps, la = a - ra * Ps;
+      if (ra == sp.rank) {
+        __stcg(rm_new + i, ldcg_i32(rm_old + (size_t)la * N + m));
+      } else if (slot == 0 || ldcg_i32(anc + sp.slot0 + slot - 1) != a + 1) {
+        // first local child of an ancestor held by another rank: its occupied rows are pulled into four
+        // fresh local rows each (the row, its child of step st+1, the two ids handed out for step st+2)
+        const int rb = ldcg_i32(on_rank(sp, rm_old, ra) + (size_t)la * N + m);
+        int d = pd.cap - 1;
+        if (rb != pd.cap - 1) {
+          const int first = spec_gclaim(pd, 4);
+          if (first < 0) { atomicExch(sp.err, 80); sm.fail = 1; }
+          else {
+            const int v2 = spec_gtake(pd, first), c2 = spec_gtake(pd, first + 1);
+            const int a2 = spec_gtake(pd, first + 2), b2 = spec_gtake(pd, first + 3);
+            const long long job = atomicAdd((unsigned long long*)&sp.counters[5], 1ull);
+            sp.pull_jobs[2 * job] = make_int4(k | (ra << 8), rb, v2, c2);
+            sp.pull_jobs[2 * job + 1] = make_int4(a2, b2, 0, 0);
+            d = v2;
+          }
+        }
+        __stcg(rm_new + i, d);
+      }
     }
+  }
+  if (sp.R > 1) {
+    if (!spec_gsync(sp, sm)) return false;
+    // pull the reserved rows (a warp per row); the other children of a remote ancestor share its first child's map
+    const long long njobs = __ldcg(&sp.counters[5]);
+    const long long gw = gt >> 5, GWp = GT >> 5;
+#pragma unroll 1
+    for (long long job = gw; job < njobs; job += GWp) spec_row_pull(sp, __ldcg(sp.pull_jobs + 2 * job), __ldcg(sp.pull_jobs + 2 * job + 1), parn);
+    if (gt == 0) sp.counters[3] += njobs;
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      int* rm_new = sp.pd[k].rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+#pragma unroll 1
+      for (long long i = gt; i < (long long)Ps * N; i += GT) {
+        const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
+        const int a1 = ldcg_i32(anc + sp.slot0 + slot);
+        if ((a1 - 1) / Ps == sp.rank) continue;
+        int f = slot;
+        while (f > 0 && ldcg_i32(anc + sp.slot0 + f - 1) == a1) --f;
+        if (f != slot) __stcg(rm_new + i, ldcg_i32(rm_new + (size_t)f * N + m));
+      }
+    }
+    if (!spec_gsync(sp, sm)) return false;
+    if (gt == 0) sp.counters[5] = 0;
+  }
+#pragma unroll 1
+  for (int k = 0; k < K; ++k) {
+    const PoolDev& pd = sp.pd[k];
     int* rc_new = pd.refcnt + (size_t)parn * pd.cap;
 #pragma unroll 1
     for (long long r = gt; r < pd.cap; r += GT) {
@@ -747,7 +915,7 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
       }
     }
   }
-  if (!spec_gsync(sp, sm)) return false;
+  if (!spec_xsync(sp, sm)) return false;  // no rank recycles a row while a peer may still be pulling it
   if (gt == 0 && has_next) atomicAdd((unsigned long long*)&sp.counters[4], (unsigned long long)(-(long long)ldcg_i32(sp.gcnt)));
   if (threadIdx.x == 0) { sm.ev = ev + 1; sm.res_flag = 0; }
   __syncthreads();
@@ -804,7 +972,8 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
   if (tid < 8) sm.tacc[tid] = 0;
   if (tid < POOL_NW) sm.tr_n[tid] = 0;
   if (tid == 0) {
-    sm.res_flag = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.epoch = 0; sm.xepoch = 0; sm.res_mx = 0.0;
+    sm.res_flag = 0; sm.fail = 0; sm.ev = 0; sm.pdone = 0; sm.res_mx = 0.0;
+    sm.epoch = __ldcg(sp.bar_state); sm.xepoch = __ldcg(sp.bar_state + 1);  // the counters run on from the previous sweep
     sm.lpar = 0; sm.cnt = 0;
     for (int b = 0; b < sp.obs_ring; ++b) mbar_init(&sm.obs_bar[b], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -919,6 +1088,9 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
       sp.lw_out[p] = final_res ? 1.0 : __ldcg(on_rank(sp, sp.lw + p, p / sp.Ps));
   if (timing && tid < 8) sp.phase_ns[(size_t)cta * 8 + tid] = sm.tacc[tid] / NW;
   if (cta == 0 && tid == 0) sp.counters[2] = sm.ev;
+  // the peers' stores into this rank's allocation log have landed before the finish kernel reads it
+  if (sp.R > 1) spec_xsync(sp, sm);
+  if (cta == 0 && tid == 0) { sp.bar_state[0] = sm.epoch; sp.bar_state[1] = sm.xepoch; }  // where the next sweep's counters start
 #undef PHASE_MARK
 }
 

@@ -2,7 +2,7 @@
 # 2-GPU box: sharded parity tests, then the bench at N=2
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests/test_gpu_sharded.py -x -q -m gpu 2>&1 | tail -3
-timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/f_bench2.json 2> gpurun_out/f_bench2.err; echo "bench2 rc=$?"
+timeout 420 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 5 --warmup 3 > gpurun_out/f_bench2.json 2> gpurun_out/f_bench2.err; echo "bench2 rc=$?"
 tail -5 gpurun_out/f_bench2.err | cut -c1-300
 python - <<'PY'
 import json
