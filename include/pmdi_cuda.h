@@ -149,6 +149,9 @@ typedef struct pmdi_sweep_out {
   int64_t  rows_added[8]; /* per dataset: clusters that had an observation added (the reference's cluster_add!
                              calls, src/pmdi.jl:275-310: one per DISTINCT chosen cluster and step; dense: one per
                              particle and step)                                                    */
+  int64_t* contingency;   /* K(K-1)/2 tables of N x N (column-major, pair order as pair_agree): entry (la, lb) of
+                             pair (a, b), a < b = observations with label la in dataset a and lb in dataset b under
+                             the NEW allocations - everything align_labels! (src/misc.jl:61-108) counts; may be NULL */
 } pmdi_sweep_out;
 
 /*
@@ -185,6 +188,17 @@ int pmdi_feature_select(pmdi_ctx* ctx, int32_t k, const int64_t* labels,
  */
 int pmdi_cluster_eval(pmdi_ctx* ctx, int32_t k, const int64_t* rows, int64_t m, int64_t obs,
                       double* out_logprob, double* out_logmarg_D);
+
+/*
+ * Posterior similarity matrices on the device (src/output_analysis/consensus_map.jl:31-65: for every
+ * retained iteration and dataset, psm[i, j] += (s[i] == s[j])).
+ *   pmdi_psm_begin  zeroes K accumulators of n_obs x n_obs counts on the context's device
+ *   pmdi_psm_add    adds one allocation matrix (n_obs x K column-major, labels 1..N)
+ *   pmdi_psm_get    out[k][i][j] = count / samples as doubles (K * n_obs * n_obs values)
+ */
+int pmdi_psm_begin(pmdi_ctx* ctx);
+int pmdi_psm_add(pmdi_ctx* ctx, const int64_t* s);
+int pmdi_psm_get(pmdi_ctx* ctx, double* out);
 
 /* The uniform the sweep uses for (kind, step, k, index); kinds as in the sweep:
    0 allocation, 1 resampling offset, 2 shuffle pick, 3 selection, 4 feature flag. */

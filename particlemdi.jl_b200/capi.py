@@ -28,6 +28,7 @@ EXPORTS = [
     "pmdi_sweep", "pmdi_sweep_upload", "pmdi_sweep_run", "pmdi_sweep_download",
     "pmdi_feature_null", "pmdi_feature_select", "pmdi_cluster_eval", "pmdi_uniform",
     "pmdi_ctx_set_ranks", "pmdi_ipc_export", "pmdi_ipc_import",
+    "pmdi_psm_begin", "pmdi_psm_add", "pmdi_psm_get",
 ]
 IPC_HANDLE_BYTES = 64
 
@@ -64,7 +65,7 @@ class SweepOut(C.Structure):
         ("dbg_anc", C.c_void_p), ("cluster_n", C.c_void_p),
         ("label_counts", C.c_void_p), ("pair_agree", C.c_void_p),
         ("rows_referenced", C.c_int64 * 8), ("engine", C.c_int32), ("rows_evaluated_ahead", C.c_int64),
-        ("rows_computed", C.c_int64 * 8), ("rows_added", C.c_int64 * 8),
+        ("rows_computed", C.c_int64 * 8), ("rows_added", C.c_int64 * 8), ("contingency", C.c_void_p),
     ]
 
 
@@ -102,6 +103,9 @@ def lib():
         L.pmdi_ctx_set_ranks.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.pmdi_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
         L.pmdi_ipc_import.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.pmdi_psm_begin.argtypes = [C.c_void_p]
+        L.pmdi_psm_add.argtypes = [C.c_void_p, C.c_void_p]
+        L.pmdi_psm_get.argtypes = [C.c_void_p, C.c_void_p]
         L.pmdi_uniform.restype = C.c_double
         L.pmdi_uniform.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                    C.c_uint32]
@@ -261,9 +265,12 @@ class Context:
             "cluster_n": np.zeros((K, P, N), dtype=np.int64),
             "label_counts": np.zeros((N, K), dtype=np.int64, order="F"),
             "pair_agree": np.zeros(max(1, K * (K - 1) // 2), dtype=np.int64),
+            # [pair][lb][la]: entry (la, lb) of an N x N column-major table per dataset pair
+            "contingency": np.zeros((max(1, K * (K - 1) // 2), N, N), dtype=np.int64),
         }
         o = SweepOut()
         o.label_counts, o.pair_agree = _ptr(res["label_counts"]), _ptr(res["pair_agree"])
+        o.contingency = _ptr(res["contingency"])
         o.s, o.p_star, o.logweight = _ptr(res["s"]), _ptr(res["p_star"]), _ptr(res["logweight"])
         o.cluster_n = _ptr(res["cluster_n"])
         if debug:
@@ -320,6 +327,18 @@ class Context:
         o, res = self._out(self._steps, self._debug)
         _check(lib().pmdi_sweep_download(self.h, C.byref(o)))
         return self._finish(o, res)
+
+    # ---- posterior similarity matrices (consensus_map.jl:31-65) --------------------------------
+    def psm(self, alloc):
+        """alloc: (rows, n_obs, K) retained allocations -> (K, n_obs, n_obs) on the GPU."""
+        alloc = np.asarray(alloc)
+        _check(lib().pmdi_psm_begin(self.h))
+        for r in range(alloc.shape[0]):
+            s = np.asfortranarray(alloc[r], dtype=np.int64)
+            _check(lib().pmdi_psm_add(self.h, _ptr(s)))
+        out = np.zeros((self.K, self.n, self.n))
+        _check(lib().pmdi_psm_get(self.h, _ptr(out)))
+        return out
 
     # ---- feature selection / plugin contract -------------------------------------------------
     def feature_null(self, k):

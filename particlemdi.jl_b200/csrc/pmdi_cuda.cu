@@ -133,7 +133,10 @@ struct pmdi_ctx {
   DevBuf<int2> copies;
   DevBuf<unsigned> bar;
   DevBuf<unsigned long long> rows_eval, rows_ref, phase_ns, trace;
-  DevBuf<long long> label_counts, pair_agree;
+  DevBuf<long long> label_counts, pair_agree, contingency;
+  DevBuf<unsigned> psm;
+  DevBuf<long long> psm_s;
+  long long psm_samples = 0;
   DevBuf<double> rank_part;
   DevBuf<int4> pull_jobs;
   DevBuf<unsigned char> dec;
@@ -553,7 +556,7 @@ int pmdi_ctx_destroy(pmdi_ctx* c) {
   c->rows_eval.release(); c->phase_ns.release(); c->scratch_u8.release();
   c->dec.release(); c->rows_spec.release(); c->rows_add.release(); c->bar_state.release(); c->glist.release(); c->elist.release(); c->gcnt.release();
   c->rows_ref.release(); c->trace.release(); c->wd_state.release(); c->pull_jobs.release(); c->rank_part.release();
-  c->label_counts.release(); c->pair_agree.release();
+  c->label_counts.release(); c->pair_agree.release(); c->contingency.release(); c->psm.release(); c->psm_s.release();
   for (int r = 0; r < c->R; ++r)
     if (r != c->rank && c->peer_base[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
   if (c->arena) cudaFree(c->arena);
@@ -780,6 +783,7 @@ int pmdi_sweep_upload(pmdi_ctx* c, const pmdi_sweep_args* a) {
   CK(c->members.ensure((size_t)K * std::max<long long>(a->n1 - 1, 1))); CK(c->mem_off.ensure((size_t)K * (N + 1)));
   CK(c->cur_at.ensure(steps));
   CK(c->rows_ref.ensure(PMDI_MAX_K)); CK(c->label_counts.ensure((size_t)N * K)); CK(c->pair_agree.ensure(std::max(npairs, 1)));
+  CK(c->contingency.ensure((size_t)std::max(npairs, 1) * N * N));
   sp.rows_ref = c->rows_ref.p;
   CK(c->dec.ensure(steps)); CK(c->rows_spec.ensure(PMDI_MAX_K)); CK(c->rows_add.ensure(PMDI_MAX_K));
   CK(cudaMemsetAsync(c->rows_spec.p, 0, 8 * PMDI_MAX_K, st));
@@ -894,7 +898,7 @@ int pmdi_sweep_run(pmdi_ctx* c) {
   }
   CK(cudaEventRecord(c->ev2, st));
   k_finish_pool<<<1, 256, 0, st>>>(sp, (c->sweep_flags & PMDI_SWEEP_SSTAR_COMPAT) ? 1 : 0, c->s_out.p, c->d_pstar.p,
-                                   c->cluster_n.p, c->cur_at.p, c->label_counts.p, c->pair_agree.p);
+                                   c->cluster_n.p, c->cur_at.p, c->label_counts.p, c->pair_agree.p, c->contingency.p);
   CK(cudaGetLastError());
   CK(cudaEventRecord(c->ev3, st));
   c->sweep_seq += 1;
@@ -924,6 +928,8 @@ int pmdi_sweep_download(pmdi_ctx* c, pmdi_sweep_out* o) {
     CK(cudaMemcpyAsync(o->label_counts, c->label_counts.p, sizeof(int64_t) * N * K, cudaMemcpyDeviceToHost, st));
   if (o->pair_agree && K > 1)
     CK(cudaMemcpyAsync(o->pair_agree, c->pair_agree.p, sizeof(int64_t) * (K * (K - 1) / 2), cudaMemcpyDeviceToHost, st));
+  if (o->contingency && K > 1)
+    CK(cudaMemcpyAsync(o->contingency, c->contingency.p, sizeof(int64_t) * (K * (K - 1) / 2) * N * N, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(phase.data(), c->phase_ns.p, 8 * sizeof(unsigned long long) * c->G, cudaMemcpyDeviceToHost, st));
   CK(cudaMemcpyAsync(&pstar, c->d_pstar.p, sizeof(long long), cudaMemcpyDeviceToHost, st));
   if (o->s) CK(cudaMemcpyAsync(o->s, c->s_out.p, sizeof(int64_t) * n * K, cudaMemcpyDeviceToHost, st));
@@ -1086,6 +1092,63 @@ int pmdi_feature_select(pmdi_ctx* c, int32_t k, const int64_t* labels, const dou
   std::vector<int> w(off.begin(), off.end() - 1);
   for (long long i = 0; i < n; ++i) mem[w[order_of[labels[i]]]++] = (int)i;
   return run_logmarginal(c, k, off, mem, 0, feature_null, 1.0, 1.0, out_prob_D, out_flags_D, tape_f, seed, iter);
+}
+
+// ---------------------------------------------------------------------------------------------
+// posterior similarity matrices (src/output_analysis/consensus_map.jl:31-65)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_psm_add(const long long* s, unsigned* psm, long long n, int K) {
+  const int k = blockIdx.z;
+  const long long i = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+  const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n || j >= n) return;
+  const long long* sk = s + (size_t)k * n;
+  if (sk[i] == sk[j]) psm[((size_t)k * n + i) * n + j] += 1u;
+}
+__global__ void k_psm_get(const unsigned* psm, double* out, size_t total, double inv) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) out[i] = (double)psm[i] * inv;
+}
+
+int pmdi_psm_begin(pmdi_ctx* c) {
+  if (!c) return fail(1, "NULL context");
+  CK(cudaSetDevice(c->device));
+  const size_t total = (size_t)c->K * c->n * c->n;
+  CK(c->psm.ensure(total));
+  CK(c->psm_s.ensure((size_t)c->K * c->n));
+  CK(cudaMemsetAsync(c->psm.p, 0, sizeof(unsigned) * total, c->stream));
+  c->psm_samples = 0;
+  return 0;
+}
+
+int pmdi_psm_add(pmdi_ctx* c, const int64_t* s) {
+  if (!c || !s) return fail(1, "pmdi_psm_add: NULL argument");
+  if (!c->psm.p) return fail(1, "pmdi_psm_add: call pmdi_psm_begin first");
+  CK(cudaSetDevice(c->device));
+  for (long long i = 0; i < c->n * c->K; ++i)
+    if (s[i] < 1 || s[i] > c->N) return fail(1, "pmdi_psm_add: allocation label outside 1..N");
+  CK(cudaMemcpyAsync(c->psm_s.p, s, sizeof(int64_t) * c->n * c->K, cudaMemcpyHostToDevice, c->stream));
+  const dim3 blk(32, 8), grd((unsigned)((c->n + 31) / 32), (unsigned)((c->n + 7) / 8), (unsigned)c->K);
+  k_psm_add<<<grd, blk, 0, c->stream>>>(c->psm_s.p, c->psm.p, c->n, c->K);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));  // the host buffer may be reused by the caller
+  c->psm_samples += 1;
+  return 0;
+}
+
+int pmdi_psm_get(pmdi_ctx* c, double* out) {
+  if (!c || !out) return fail(1, "pmdi_psm_get: NULL argument");
+  if (!c->psm.p || c->psm_samples < 1) return fail(1, "pmdi_psm_get: nothing accumulated");
+  CK(cudaSetDevice(c->device));
+  const size_t total = (size_t)c->K * c->n * c->n;
+  double* d = nullptr;
+  CK(cudaMalloc((void**)&d, sizeof(double) * total));
+  k_psm_get<<<c->n_sm * 8, 256, 0, c->stream>>>(c->psm.p, d, total, 1.0 / (double)c->psm_samples);
+  cudaError_t e = cudaMemcpyAsync(out, d, sizeof(double) * total, cudaMemcpyDeviceToHost, c->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return fail(100 + (int)e, std::string("pmdi_psm_get: ") + cudaGetErrorString(e));
+  return 0;
 }
 
 int pmdi_cluster_eval(pmdi_ctx* c, int32_t k, const int64_t* rows, int64_t m, int64_t obs,

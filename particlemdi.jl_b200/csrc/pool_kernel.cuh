@@ -1060,7 +1060,8 @@ __global__ void k_pool_prefix_cat(SweepParams sp, int k, const int* members, con
 // plus the reductions the host's update_hypers reads (src/update_hypers.jl:72,109-115): label counts
 // per (label, dataset) and, per dataset pair, the number of observations with equal labels.
 __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long long* p_star_out,
-                              long long* cluster_n, int* cur_at, long long* label_counts, long long* pair_agree) {
+                              long long* cluster_n, int* cur_at, long long* label_counts, long long* pair_agree,
+                              long long* contingency) {
   const int t = threadIdx.x, NT = blockDim.x, P = sp.P, K = sp.K, N = sp.N;
   __shared__ double red[32];
   double mx = -INFINITY;
@@ -1100,6 +1101,7 @@ __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long
   for (int i = t; i < N * K; i += NT) label_counts[i] = 0;
 #pragma unroll 1
   for (int i = t; i < K * (K - 1) / 2; i += NT) pair_agree[i] = 0;
+  for (int i = t; i < K * (K - 1) / 2 * N * N; i += NT) contingency[i] = 0;
   __syncthreads();
 #pragma unroll 1
   for (int idx = t; idx < sp.steps * K; idx += NT) {
@@ -1118,8 +1120,9 @@ __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long
     for (int k1 = 0; k1 < K - 1; ++k1)
 #pragma unroll 1
       for (int k2 = k1 + 1; k2 < K; ++k2) {
-        if (s_out[(size_t)k1 * sp.n_obs + i] == s_out[(size_t)k2 * sp.n_obs + i])
-          atomicAdd((unsigned long long*)&pair_agree[idx], 1ull);
+        const int la = (int)s_out[(size_t)k1 * sp.n_obs + i] - 1, lb = (int)s_out[(size_t)k2 * sp.n_obs + i] - 1;
+        if (la == lb) atomicAdd((unsigned long long*)&pair_agree[idx], 1ull);
+        atomicAdd((unsigned long long*)&contingency[((size_t)idx * N + lb) * N + la], 1ull);
         ++idx;
       }
   }

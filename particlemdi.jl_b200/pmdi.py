@@ -94,8 +94,108 @@ class HyperTables:
         return np.exp(t)
 
 
-def update_Z(phi, tables):
+class FactorisedZ:
+    """The sums the hyper-parameter updates take over the N^K label combinations
+    (src/pmdi.jl:69-92, src/update_hypers.jl:29-39, 75-90, 101-125) WITHOUT the N^K tables.
+
+    The summand is  prod_k gamma[c_k, k] * prod_{a<b} (1 + phi_ab)^[c_a == c_b].  Expanding
+    prod (1 + phi_ab [c_a == c_b]) over subsets of pairs groups the datasets into the connected
+    components of a graph; within a component all labels are equal, so
+
+        Z = sum over set partitions {C_1..C_m} of the datasets of  prod_i conn(C_i) * s(C_i)
+
+    with s(C) = sum_l prod_{k in C} gamma[l, k] and conn(C) = sum over CONNECTED graphs on C of
+    prod phi_e, which follows from all(C) = prod_{e in C} (1 + phi_e) by the usual recursion.  All of
+    it is a DP over the 2^K subsets of datasets: O(3^K + K 2^K N) instead of O(K N^K)
+    (K = 6, N = 30: 7e8 table rows in the reference, a few thousand operations here)."""
+
+    def __init__(self, N, K):
+        self.N, self.K = N, K
+        self.full = (1 << K) - 1
+        self.pairs = phi_lab(K)
+        self.members = [[k for k in range(K) if S >> k & 1] for S in range(1 << K)]
+        # proper sub-subsets containing the lowest member, per subset
+        self.subs = []
+        for S in range(1 << K):
+            if S == 0:
+                self.subs.append([])
+                continue
+            low = S & -S
+            rest = S ^ low
+            out, T = [], rest
+            while True:  # all subsets T of rest -> component low | T
+                out.append(low | T)
+                if T == 0:
+                    break
+                T = (T - 1) & rest
+            self.subs.append(out)
+
+    def _conn(self, phi):
+        K = self.K
+        allp = np.ones(1 << K)
+        for S in range(1 << K):
+            m = self.members[S]
+            v = 1.0
+            for i, (a, b) in enumerate(self.pairs):
+                if (S >> a & 1) and (S >> b & 1):
+                    v *= 1.0 + phi[i]
+            allp[S] = v
+        conn = np.zeros(1 << K)
+        for S in range(1, 1 << K):
+            acc = allp[S]
+            for C in self.subs[S]:
+                if C != S:
+                    acc -= conn[C] * allp[S ^ C]
+            conn[S] = acc
+        return conn
+
+    def _prods(self, gamma):
+        """P_S[l] = prod_{k in S} gamma[l, k] for every subset S (P_0 = 1)."""
+        K, N = self.K, self.N
+        P = np.ones((1 << K, N))
+        for S in range(1, 1 << K):
+            low = (S & -S).bit_length() - 1
+            P[S] = P[S & (S - 1)] * gamma[:, low]
+        return P
+
+    def _F(self, g):
+        """F(S) = sum over set partitions of S of prod g(C)."""
+        F = np.zeros(1 << self.K)
+        F[0] = 1.0
+        for S in range(1, 1 << self.K):
+            F[S] = sum(g[C] * F[S ^ C] for C in self.subs[S])
+        return F
+
+    def Z(self, gamma, phi):
+        P = self._prods(gamma)
+        g = self._conn(phi) * P.sum(axis=1)
+        return float(self._F(g)[self.full])
+
+    def A(self, gamma, phi, k):
+        """A_k[n] = sum over the combinations with c_k = n of the summand, divided by gamma[n, k]
+        (what update_gamma! needs: beta_star = 1 + v * A_k[n], src/update_hypers.jl:75-81)."""
+        P = self._prods(gamma)
+        conn = self._conn(phi)
+        F = self._F(conn * P.sum(axis=1))
+        out = np.zeros(self.N)
+        bit = 1 << k
+        for C in range(1, 1 << self.K):
+            if C & bit:
+                out += conn[C] * P[C ^ bit] * F[self.full ^ C]
+        return out
+
+    def Q(self, gamma, phi, i):
+        """Q_ab = sum over the combinations with c_a == c_b of the summand, divided by (1 + phi_ab)
+        (update_Phi!: beta_star = 5 + v * Q_ab, src/update_hypers.jl:101-107).  Z is linear in phi_ab."""
+        p1, p0 = np.array(phi, dtype=float), np.array(phi, dtype=float)
+        p1[i], p0[i] = 1.0, 0.0
+        return self.Z(gamma, p1) - self.Z(gamma, p0)
+
+
+def update_Z(phi, tables, gamma=None):
     """update_Z (src/update_hypers.jl:29-39)."""
+    if isinstance(tables, FactorisedZ):
+        return tables.Z(gamma, phi)
     return float(tables.norm_terms(phi).sum())
 
 
@@ -121,13 +221,22 @@ def update_M(M, gamma, K, N, rng):
             M[k] = prop
 
 
-def update_gamma(gamma, phi, v, M, s, tables, rng):
+def update_gamma(gamma, phi, v, M, s, tables, rng, counts_all=None):
     """update_gamma! (src/update_hypers.jl:64-92): Gibbs update of every component weight, with the
-    normalising terms kept in step with the new value."""
+    normalising terms kept in step with the new value.  `counts_all` (N x K): the label counts the
+    sweep reduced on the device (countn(s[:, k], n), :72); recounted from `s` when absent."""
     N, K = tables.N, tables.K
+    if isinstance(tables, FactorisedZ):
+        for k in range(K):
+            counts = counts_all[:, k] if counts_all is not None else np.bincount(s[:, k] - 1, minlength=N)
+            A = tables.A(gamma, phi, k)  # does not depend on column k: one evaluation serves all n
+            for n in range(N):
+                beta_star = 1.0 + v * A[n]
+                gamma[n, k] = rng.gamma(M[k] / N + counts[n], 1.0 / beta_star) + EPS
+        return
     norm = tables.norm_terms(phi)
     for k in range(K):
-        counts = np.bincount(s[:, k] - 1, minlength=N)  # countn(s[:, k], n), :72
+        counts = counts_all[:, k] if counts_all is not None else np.bincount(s[:, k] - 1, minlength=N)  # countn(s[:, k], n), :72
         col = tables.combn[:, k]
         for n in range(N):
             rows = col == n
@@ -137,23 +246,29 @@ def update_gamma(gamma, phi, v, M, s, tables, rng):
             norm[rows] *= gamma[n, k] / old
 
 
-def update_phi(phi, v, s, tables, rng):
+def update_phi(phi, v, s, tables, rng, agree_all=None, gamma=None):
     """update_Phi! (src/update_hypers.jl:95-128): each Phi is drawn from a mixture of Gammas indexed
     by 0..n_agree, prior shape 1 and rate 5.  The weight of component j is restated literally from
-    :118-120, including ``- j * log(1 / beta_star)``."""
+    :118-120, including ``- j * log(1 / beta_star)``.  `agree_all`: the per-pair agreement counts the
+    sweep reduced on the device (:109-115)."""
     K = tables.K
-    norm = tables.norm_terms(phi)
+    fact = isinstance(tables, FactorisedZ)
+    norm = None if fact else tables.norm_terms(phi)
     for i, (a, b) in enumerate(phi_lab(K)):
         cur = phi[i]
-        n_agree = int((s[:, a] == s[:, b]).sum())
-        rows = tables.phi_index[:, i]
-        beta_star = 5.0 + v * norm[rows].sum() / (1.0 + cur)
+        n_agree = int(agree_all[i]) if agree_all is not None else int((s[:, a] == s[:, b]).sum())
+        if fact:
+            beta_star = 5.0 + v * tables.Q(gamma, phi, i)
+        else:
+            rows = tables.phi_index[:, i]
+            beta_star = 5.0 + v * norm[rows].sum() / (1.0 + cur)
         j = np.arange(n_agree + 1)
         w = special.gammaln(j + 1.0) + stats.binom.logpmf(j, n_agree, 0.5) - j * math.log(1.0 / beta_star)
         w = np.exp(w - w.max())
         alpha_star = 1.0 + rng.choice(n_agree + 1, p=w / w.sum())
         phi[i] = rng.gamma(alpha_star, 1.0 / beta_star)
-        norm[rows] *= (1.0 + phi[i]) / (1.0 + cur)
+        if not fact:
+            norm[rows] *= (1.0 + phi[i]) / (1.0 + cur)
 
 
 def align_labels(s, phi, gamma, N, K, rng):
@@ -187,6 +302,62 @@ def align_labels(s, phi, gamma, N, K, rng):
                     gamma[[new_label - 1, label - 1], k] = gamma[[label - 1, new_label - 1], k]
                     label = new_label
                     rows_l = np.flatnonzero(s[:, k] == label)
+
+
+def align_labels_tables(s, cont, phi, gamma, N, K, rng):
+    """align_labels! (src/misc.jl:61-108) from the contingency tables the sweep reduced on the
+    device (`cont[pair][lb][la]` = observations with label la+1 in dataset a and lb+1 in dataset b):
+    every count the Metropolis test needs is an entry of a table, a swap exchanges two rows (or
+    columns) of the tables, and the allocations are relabelled once at the end - no pass over the
+    n observations per proposal.  Same proposals, same random numbers, same result as
+    :func:`align_labels`.  Returns (label counts N x K, per-pair agreement counts) after alignment."""
+    pairs = phi_lab(K)
+    phi_log = np.log(np.asarray(phi) + 1.0)
+    # M[(a, b)][la, lb] for a < b
+    M = {pr: np.array(cont[i], dtype=np.int64).T.copy() for i, pr in enumerate(pairs)}
+    for k in range(K):
+        others = [j for j in range(K) if j != k]
+        rel = np.array([phi_log[i] for i, (a, b) in enumerate(pairs) if a == k or b == k])
+        # T[j_index][l, lab] = observations with label l in dataset k and lab in dataset j
+        T = np.stack([M[(k, j)] if k < j else M[(j, k)].T for j in others]).astype(np.float64)
+        W = np.zeros((N, N))  # W[l, lab] = sum_j rel_j * T_j[l, lab], summed in dataset order like the reference
+        for ji in range(len(others)):
+            W = W + T[ji] * rel[ji]
+        size = T[0].sum(axis=1)  # members of every label of dataset k
+        perm = np.arange(N)      # perm[old label index] = current label index
+        order = list(dict.fromkeys(s[:, k].tolist()))  # unique(), first-appearance order (1-based)
+        for lab0 in order:
+            # the reference tests `s[:, k] == label` with the label VALUE: after earlier swaps that value may
+            # hold another group's members or nobody
+            label = lab0 - 1
+            if size[label] == 0:
+                continue
+            for new_label in range(N):
+                if new_label == label:
+                    continue
+                keep = W[label, label] + W[new_label, new_label]
+                swap = W[label, new_label] + W[new_label, label]
+                if rng.random() < math.exp(min(swap - keep, 50.0)):
+                    W[[label, new_label]] = W[[new_label, label]]
+                    T[:, [label, new_label]] = T[:, [new_label, label]]
+                    size[[label, new_label]] = size[[new_label, label]]
+                    gamma[[new_label, label], k] = gamma[[label, new_label], k]
+                    # members that carried `label` now carry `new_label` and vice versa
+                    a_, b_ = perm == label, perm == new_label
+                    perm[a_], perm[b_] = new_label, label
+                    label = new_label
+        s[:, k] = perm[s[:, k] - 1] + 1
+        for ji, j in enumerate(others):  # the other datasets see dataset k's new labels
+            if k < j:
+                M[(k, j)] = T[ji].astype(np.int64)
+            else:
+                M[(j, k)] = T[ji].T.astype(np.int64)
+    counts = np.zeros((N, K), dtype=np.int64)
+    for k in range(K):
+        j = 0 if k else 1
+        counts[:, k] = M[(k, j)].sum(axis=1) if k < j else M[(j, k)].sum(axis=0)
+    agree = np.array([int(np.trace(M[pr])) for pr in pairs], dtype=np.int64)
+    return counts, agree
 
 
 # ------------------------------------------------------------------ CSV (src/pmdi.jl:147-158,377-383)
@@ -244,7 +415,8 @@ def posterior_similarity(alloc):
 
 # ------------------------------------------------------------------ the entry point
 def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, featureSelect=None,
-         dataNames=None, seed=0, device=0, stale_gamma_table=False, sstar_compat=False):
+         dataNames=None, seed=0, device=0, stale_gamma_table=False, sstar_compat=False, factorised=None,
+         device_reductions=True):
     """``pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile; thin, featureSelect,
     dataNames)`` of src/pmdi.jl:36-40.  Side effect: the CSV file(s); returns a small dict of
     timings and counters (the reference returns nothing)."""
@@ -274,11 +446,18 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
     phi = rng.gamma(1.0, 0.2, npairs) if K > 1 else np.zeros(1)   # :61
     s = np.stack([1 + rng.choice(N, size=n_obs, p=gamma[:, k] / gamma[:, k].sum())
                   for k in range(K)], axis=1).astype(np.int64)    # :63-66
-    tables = HyperTables(N, K)                                    # :69-92
-    tables.refresh(gamma)
-    Z = update_Z(phi, tables)                                     # :95
+    # the N^K-row tables of :69-92 where they are small, the factorised sums (FactorisedZ) otherwise
+    if factorised is None:
+        factorised = N ** K > 200_000
+    if factorised and stale_gamma_table:
+        raise ValueError("stale_gamma_table needs the literal N^K tables")
+    tables = FactorisedZ(N, K) if factorised else HyperTables(N, K)
+    if not factorised:
+        tables.refresh(gamma)
+    Z = update_Z(phi, tables, gamma)                              # :95
     v = update_v(n_obs, Z, rng)                                   # :96
 
+    counts = agree = None  # first iteration: counted from the initial allocation
     ctx = capi.Context(dataFiles, types, N, particles, device=device)  # raises without a GPU
     stats_out = dict(sweep_device_ms=0.0, n_resamples=0, iterations=0)
     ffile = None
@@ -300,15 +479,15 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
             for it in range(1, iter + 1):                         # :164
                 order_obs = rng.permutation(n_obs) + 1            # :172
                 update_M(M, gamma, K, N, rng)                     # :176
-                if not stale_gamma_table:
+                if not stale_gamma_table and not factorised:
                     tables.refresh(gamma)
-                update_gamma(gamma, phi, v, M, s, tables, rng)    # :177
+                update_gamma(gamma, phi, v, M, s, tables, rng, counts_all=counts)    # :177
                 Pi = gamma / gamma.sum(axis=0, keepdims=True)     # :179
-                if not stale_gamma_table:
+                if not stale_gamma_table and not factorised:
                     tables.refresh(gamma)
                 if K > 1:
-                    update_phi(phi, v, s, tables, rng)            # :181-183
-                Z = update_Z(phi, tables)                         # :184
+                    update_phi(phi, v, s, tables, rng, agree_all=agree, gamma=gamma)  # :181-183
+                Z = update_Z(phi, tables, gamma)                  # :184
                 v = update_v(n_obs, Z, rng)                       # :185
                 r = ctx.sweep(s, order_obs, n1, Pi, phi if K > 1 else None,
                               logweight_init=0.0 if it == 1 else 1.0,   # :99, :372
@@ -321,7 +500,15 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
                         _, fl = ctx.feature_select(k, s[:, k], feature_null[k], seed=seed, it=it)
                         flags[k] = fl.astype(bool)
                         ctx.set_flags(k, fl)
-                align_labels(s, phi, gamma, N, K, rng)            # :375
+                # :375 - and the counts the next update_gamma! / update_Phi! read (update_hypers.jl:72,109-115),
+                # from the tables the sweep reduced on the device
+                if not device_reductions:
+                    align_labels(s, phi, gamma, N, K, rng)
+                    counts = agree = None
+                elif K > 1:
+                    counts, agree = align_labels_tables(s, r["contingency"], phi, gamma, N, K, rng)
+                else:
+                    counts, agree = np.array(r["label_counts"]), None
                 ll = time.perf_counter() - t0                     # :377 (cumulative seconds)
                 if it % thin == 0:                                # :378-383
                     out.write(csv_row(M, phi, ll, s) + "\n")

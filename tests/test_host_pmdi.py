@@ -132,3 +132,88 @@ def test_hyper_updates_keep_state_valid():
         v = host.update_v(n, Z, rng)
         assert (gamma > 0).all() and (phi >= 0).all() and (M > 0).all() and Z > 0 and v > 0
         assert np.isfinite(gamma).all() and np.isfinite(phi).all()
+
+
+@pytest.mark.parametrize("N,K", [(3, 2), (4, 3), (3, 4), (2, 5)])
+def test_factorised_sums_equal_the_table_sums(N, K):
+    """FactorisedZ (no N^K tables) against the literal tables of src/pmdi.jl:69-92: Z (update_hypers.jl:29-39),
+    the per-(n, k) sums update_gamma! takes (:75-81) and the per-pair sums update_Phi! takes (:101-107)."""
+    rng = np.random.default_rng(N * 10 + K)
+    gamma = rng.gamma(1.0, 1.0, (N, K)) + 0.1
+    phi = rng.gamma(1.0, 0.5, max(1, K * (K - 1) // 2))
+    t = host.HyperTables(N, K)
+    t.refresh(gamma)
+    f = host.FactorisedZ(N, K)
+    norm = t.norm_terms(phi)
+    np.testing.assert_allclose(f.Z(gamma, phi), norm.sum(), rtol=1e-12)
+    for k in range(K):
+        want = np.array([norm[t.combn[:, k] == n].sum() / gamma[n, k] for n in range(N)])
+        np.testing.assert_allclose(f.A(gamma, phi, k), want, rtol=1e-11)
+    for i in range(K * (K - 1) // 2):
+        want = norm[t.phi_index[:, i]].sum() / (1.0 + phi[i])
+        np.testing.assert_allclose(f.Q(gamma, phi, i), want, rtol=1e-10)
+
+
+def test_factorised_handles_config3():
+    """BASELINE config 3 (N = 30, K = 6: 7.29e8 table rows in the reference) is a DP over 64 subsets."""
+    rng = np.random.default_rng(0)
+    gamma = rng.gamma(1.0 / 30, 1.0, (30, 6)) + 1e-6
+    phi = rng.gamma(1.0, 0.2, 15)
+    f = host.FactorisedZ(30, 6)
+    Z = f.Z(gamma, phi)
+    assert np.isfinite(Z) and Z > 0
+    # multilinearity: Z = sum_n gamma[n, k] * A_k[n] for every k
+    for k in range(6):
+        np.testing.assert_allclose((gamma[:, k] * f.A(gamma, phi, k)).sum(), Z, rtol=1e-10)
+
+
+def test_factorised_updates_follow_the_table_updates():
+    """The same random stream through update_gamma! / update_Phi! with the tables and with the factorised sums."""
+    N, K, n = 4, 3, 40
+    rng0 = np.random.default_rng(5)
+    s = rng0.integers(1, N + 1, (n, K))
+    g0 = rng0.gamma(1.0, 1.0, (N, K)) + 0.1
+    p0 = rng0.gamma(1.0, 0.2, 3)
+    M = np.full(K, 2.0)
+    out = []
+    for fact in (False, True):
+        gamma, phi = g0.copy(), p0.copy()
+        tables = host.FactorisedZ(N, K) if fact else host.HyperTables(N, K)
+        rng = np.random.default_rng(9)
+        for _ in range(3):
+            if not fact:
+                tables.refresh(gamma)
+            host.update_gamma(gamma, phi, 0.7, M, s, tables, rng)
+            if not fact:
+                tables.refresh(gamma)
+            host.update_phi(phi, 0.7, s, tables, rng, gamma=gamma)
+        out.append((gamma, phi))
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-9)
+    np.testing.assert_allclose(out[0][1], out[1][1], rtol=1e-9)
+
+
+@pytest.mark.parametrize("K", [2, 3, 4])
+def test_align_labels_from_tables_equals_align_labels(K):
+    """align_labels! driven by contingency tables (what the sweep reduces on the device) makes the same
+    proposals with the same random numbers as the pass over the observations (src/misc.jl:61-108)."""
+    N, n = 6, 90
+    rng0 = np.random.default_rng(K)
+    base = rng0.integers(1, 4, n)
+    s0 = np.stack([np.where(rng0.random(n) < 0.8, (base + k) % 3 + 1, rng0.integers(1, N + 1, n)) for k in range(K)], axis=1)
+    phi = rng0.gamma(2.0, 2.0, K * (K - 1) // 2)
+    g0 = rng0.gamma(1.0, 1.0, (N, K))
+    pairs = host.phi_lab(K)
+    cont = np.zeros((len(pairs), N, N), dtype=np.int64)
+    for i, (a, b) in enumerate(pairs):
+        np.add.at(cont[i], (s0[:, b] - 1, s0[:, a] - 1), 1)   # [pair][lb][la], the device's layout
+    s1, g1 = s0.copy(), g0.copy()
+    host.align_labels(s1, phi, g1, N, K, np.random.default_rng(3))
+    s2, g2 = s0.copy(), g0.copy()
+    counts, agree = host.align_labels_tables(s2, cont, phi, g2, N, K, np.random.default_rng(3))
+    assert (s1 != s0).any()  # labels did move
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(g1, g2)
+    for k in range(K):
+        np.testing.assert_array_equal(counts[:, k], np.bincount(s2[:, k] - 1, minlength=N))
+    for i, (a, b) in enumerate(pairs):
+        assert agree[i] == (s2[:, a] == s2[:, b]).sum()
