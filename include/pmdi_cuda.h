@@ -190,6 +190,29 @@ int pmdi_cluster_eval(pmdi_ctx* ctx, int32_t k, const int64_t* rows, int64_t m, 
                       double* out_logprob, double* out_logmarg_D);
 
 /*
+ * User-defined cluster types as device functors (the reference's plugin contract, README.md:48-88 and the
+ * dispatch sites src/pmdi.jl:122,189,219,300,365: a user struct with calc_logprob / cluster_add! /
+ * calc_logmarginal).  `cuda_src` is CUDA C++ source that defines a struct named `struct_name` with
+ *
+ *   static constexpr int WORDS;                                         doubles of state per feature (1..8)
+ *   __device__ static void   init(double* st);                          the empty cluster
+ *   __device__ static double logprob(const double* st, int n, double x);   this feature's term of calc_logprob
+ *                                                                       (n = cluster size, x = the observation)
+ *   __device__ static void   add(double* st, int n, double x);          cluster_add!; n = size AFTER the add
+ *   __device__ static double logmarginal(const double* st, int n);      this feature's calc_logmarginal
+ *
+ * (every cluster type of the reference has this form: feature-wise sufficient statistics, log-probability a sum
+ * over features).  elem_kind: PMDI_F64 or PMDI_I64, the element type of the data the type is bound to.
+ * Returns the type tag (>= 16) for pmdi_set_dataset.  The source is compiled (NVRTC, sm_100a) together with a
+ * private copy of this library's kernels when a context first uses the type; a compile error is reported then,
+ * with the compiler's log in pmdi_last_error().  One user type per context; single GPU; pool engine.
+ */
+int pmdi_register_cluster_type(const char* name, const char* cuda_src, const char* struct_name, int32_t elem_kind,
+                               int32_t* out_tag);
+/* Compiles a registered type now (no GPU needed) and reports the compiler's verdict; the log is in pmdi_last_error(). */
+int pmdi_cluster_type_check(int32_t tag);
+
+/*
  * Posterior similarity matrices on the device (src/output_analysis/consensus_map.jl:31-65: for every
  * retained iteration and dataset, psm[i, j] += (s[i] == s[j])).
  *   pmdi_psm_begin  zeroes K accumulators of n_obs x n_obs counts on the context's device

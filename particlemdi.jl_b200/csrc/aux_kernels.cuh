@@ -7,7 +7,7 @@
 
 // all rows of a dataset to the empty-cluster state (constructors gaussian_cluster.jl:17-21,
 // categorical_cluster.jl:6-10, negbinom_cluster.jl:9-10)
-__global__ void k_init_rows(DsDev ds, long long rows) {
+extern "C" __global__ void k_init_rows(DsDev ds, long long rows) {
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (ds.type == T_GAUSSIAN) {
@@ -16,6 +16,10 @@ __global__ void k_init_rows(DsDev ds, long long rows) {
     }
   } else if (ds.type == T_CATEGORICAL) {
     for (long long i = t0; i < rows * ds.Lmax * ds.Dp; i += stride) ds.cnt[i] = 0u;
+#ifdef PMDI_USER_STRUCT
+  } else if (ds.type == T_USER) {
+    for (long long i = t0; i < rows * ds.Dp; i += stride) user_build_feature(ds, i / ds.Dp, (int)(i % ds.Dp), nullptr, 0, false);
+#endif
   } else {
     for (long long i = t0; i < rows * ds.Dp; i += stride) ds.S[i] = 0;
   }
@@ -23,7 +27,7 @@ __global__ void k_init_rows(DsDev ds, long long rows) {
   for (long long i = t0; i < rows; i += stride) ds.n[i] = 0;
 }
 
-__global__ void k_sweep_init(SweepParams sp) {
+extern "C" __global__ void k_sweep_init(SweepParams sp) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < sp.P) {
     sp.slot_of[t] = t;
@@ -41,7 +45,7 @@ __global__ void k_sweep_init(SweepParams sp) {
 
 // Members of every label among the first n1-1 shuffled observations, in shuffle order
 // (src/pmdi.jl:193,200-206).  One block per dataset, thread m = label m+1.
-__global__ void k_prefix_lists(SweepParams sp, int* members /* [K][n1-1] */, int* off /* [K][N+1] */) {
+extern "C" __global__ void k_prefix_lists(SweepParams sp, int* members /* [K][n1-1] */, int* off /* [K][N+1] */) {
   const int k = blockIdx.x, m = threadIdx.x, N = sp.N, npre = sp.n1 - 1;
   __shared__ int cnt[PMDI_MAX_N + 1];
   const long long* s = sp.s_in + (size_t)k * sp.n_obs;
@@ -71,6 +75,9 @@ __global__ void k_prefix_lists(SweepParams sp, int* members /* [K][n1-1] */, int
 __device__ __forceinline__ void build_row_feature(const DsDev& ds, const PoolDev* pd, long long row, int q,
                                                   const int* mem, int cnt, int use_flags) {
   const bool on = use_flags ? (ds.flag[q] != 0) : (q < ds.D);
+#ifdef PMDI_USER_STRUCT
+  if (ds.type == T_USER) { user_build_feature(ds, row, q, mem, cnt, on); return; }
+#endif
   if (ds.type == T_GAUSSIAN) {
     double sum = 0.0, beta = 0.5, mu = 0.0, lam = 1.0;
     if (on) {
@@ -123,7 +130,7 @@ __device__ __forceinline__ void build_row_feature(const DsDev& ds, const PoolDev
 }
 
 // grid (ceil(Dp/128), N, K): prototypes of the prefix clusters into slot P
-__global__ void k_prefix_build(SweepParams sp, const int* members, const int* off) {
+extern "C" __global__ void k_prefix_build(SweepParams sp, const int* members, const int* off) {
   const int k = blockIdx.z, m = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
   const DsDev& ds = sp.ds[k];
   if (q >= ds.Dp) return;
@@ -134,7 +141,7 @@ __global__ void k_prefix_build(SweepParams sp, const int* members, const int* of
 }
 
 // aux of the prototype rows: grid (N, K), one warp per feature block
-__global__ void k_proto_aux(SweepParams sp) {
+extern "C" __global__ void k_proto_aux(SweepParams sp) {
   const int k = blockIdx.y, m = blockIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const DsDev& ds = sp.ds[k];
   const long long row = sp.proto_base + m;
@@ -147,7 +154,7 @@ __global__ void k_proto_aux(SweepParams sp) {
 }
 
 // every particle starts the sweep with the prototypes (src/pmdi.jl:197-199: particle[u,:,k] .= id)
-__global__ void k_broadcast(SweepParams sp) {
+extern "C" __global__ void k_broadcast(SweepParams sp) {
   const int lane = threadIdx.x & 31;
   const long long gw = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const long long GW = ((long long)gridDim.x * blockDim.x) >> 5;
@@ -166,7 +173,7 @@ __global__ void k_broadcast(SweepParams sp) {
 // categorical_cluster.jl:53-66, negbinom_cluster.jl:53-60.
 //   out[q] = base[q]*base_sign + sum_c logmarginal_c[q];  flags_out[q] = (1 - 1/exp(out+1)) > u_q
 // ------------------------------------------------------------------------------------------
-__global__ void k_logmarginal(DsDev ds, int n_clusters, const int* c_off, const int* members,
+extern "C" __global__ void k_logmarginal(DsDev ds, int n_clusters, const int* c_off, const int* members,
                               const double* gauss_cst /* per cluster */, const double* nlevels,
                               int use_flags,
                               const double* base, double base_scale, double out_scale, double* out,
@@ -181,6 +188,19 @@ __global__ void k_logmarginal(DsDev ds, int n_clusters, const int* c_off, const 
     const int cnt = c_off[c + 1] - c_off[c];
     const double n = (double)cnt;
     double lm;
+#ifdef PMDI_USER_STRUCT
+    if (ds.type == T_USER) {
+      double st[PmdiUser::WORDS];
+      PmdiUser::init(st);
+      if (on)
+        for (int t = 0; t < cnt; ++t) {
+          const double xv = ds.uW < 0 ? (double)((const int*)ds.x)[(size_t)mem[t] * ds.Dp + q]
+                                      : ((const double*)ds.x)[(size_t)mem[t] * ds.Dp + q];
+          PmdiUser::add(st, t + 1, xv);
+        }
+      lm = PmdiUser::logmarginal(st, cnt);
+    } else
+#endif
     if (ds.type == T_GAUSSIAN) {
       double sum = 0.0, beta = 0.5, mu = 0.0;
       const double* x = (const double*)ds.x;
@@ -225,11 +245,11 @@ __global__ void k_logmarginal(DsDev ds, int n_clusters, const int* c_off, const 
 
 // calc_logprob of observation `obs` against the prototype row (slot P, label 0), through the
 // same block operators the sweep uses.  One warp; dynamic smem = staged observation row.
-__global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
+extern "C" __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
   extern __shared__ __align__(16) unsigned char xs_raw[];
   const DsDev& ds = sp.ds[k];
   const int lane = threadIdx.x;
-  if (ds.type == T_GAUSSIAN) {
+  if (PMDI_XBYTES(ds) == 8u) {
     const double* src = (const double*)ds.x + (size_t)obs * ds.Dp;
     for (int q = lane; q < ds.Dp; q += 32) ((double*)xs_raw)[q] = src[q];
   } else {
@@ -243,6 +263,15 @@ __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
   double acc = ds.rc[n];
   for (int j = 0; j < ds.J; ++j) {
     double v;
+#ifdef PMDI_USER_STRUCT
+    if (ds.type == T_USER) {
+      const int fo = j * ds.FB + 2 * lane;
+      const int nits = min(ds.FB / PMDI_WF, (ds.Dp - j * ds.FB) / PMDI_WF);
+      double unused;
+      v = user_block(ds, ds.ust + (long long)row * PmdiUser::WORDS * ds.Dp + fo, 0, ds.flag + fo, nits, 0, n, 0u,
+                     (unsigned)__cvta_generic_to_shared(xs_raw) + fo * (ds.uW < 0 ? 4u : 8u), &unused);
+    } else
+#endif
     if (ds.type == T_GAUSSIAN) v = gauss_eval_block(ds, row, j, n, (const double*)xs_raw, lane);
     else if (ds.type == T_CATEGORICAL && sp.engine) {
       const PoolDev& pd = sp.pd[k];
@@ -260,7 +289,7 @@ __global__ void k_eval_row(SweepParams sp, int k, int obs, double* out) {
 }
 
 // single-label prefix build used by pmdi_cluster_eval: members -> prototype row 0 of slot P
-__global__ void k_build_one(SweepParams sp, int k, const int* members, int cnt) {
+extern "C" __global__ void k_build_one(SweepParams sp, int k, const int* members, int cnt) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   const DsDev& ds = sp.ds[k];
   if (q >= ds.Dp) return;
@@ -268,7 +297,7 @@ __global__ void k_build_one(SweepParams sp, int k, const int* members, int cnt) 
   build_row_feature(ds, sp.engine ? &sp.pd[k] : nullptr, row, q, members, cnt, 1);
   if (q == 0) ds.n[row] = cnt;
 }
-__global__ void k_aux_one(SweepParams sp, int k) {
+extern "C" __global__ void k_aux_one(SweepParams sp, int k) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const DsDev& ds = sp.ds[k];
   const long long row = sp.proto_base;
@@ -284,7 +313,7 @@ __global__ void k_aux_one(SweepParams sp, int k) {
 // only): lp_empty[step][k] = calc_logprob(x_step, empty cluster of dataset k).  Every label with
 // n == 0 of every particle shares this value.  One block per step; the same block operators as
 // the sweep, applied to the shared empty row.
-__global__ void k_empty_lp(SweepParams sp, double* lp_empty) {
+extern "C" __global__ void k_empty_lp(SweepParams sp, double* lp_empty) {
   extern __shared__ __align__(16) unsigned char xs_raw[];
   __shared__ double part[PMDI_MAX_K][32];
   const int step = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
@@ -319,7 +348,7 @@ __global__ void k_empty_lp(SweepParams sp, double* lp_empty) {
 
 // Observation matrix with the feature flags folded in (the sweep stages rows with plain async
 // copies): unflagged / padded features become level 0 (categorical) or -1 (NegBinom).
-__global__ void k_mark_x(const int* x, const uint8_t* flag, int* xq, long long n, int Dp, int skip) {
+extern "C" __global__ void k_mark_x(const int* x, const uint8_t* flag, int* xq, long long n, int Dp, int skip) {
   const long long total = n * Dp, stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
     xq[i] = flag[i % Dp] ? x[i] : skip;

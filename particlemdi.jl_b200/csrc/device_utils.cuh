@@ -1,8 +1,12 @@
 // Device helpers for libpmdi_cuda.so (sm_100a): RNG addressing, warp/block reductions,
 // log-factorial lookup, cache-bypassing loads for data other CTAs write, the grid barrier.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#else
+#define INFINITY (__longlong_as_double(0x7ff0000000000000LL))
+#endif
 
 #include "pmdi_internal.h"
 

@@ -15,7 +15,15 @@
  */
 #ifndef PMDI_INTERNAL_H
 #define PMDI_INTERNAL_H
+#ifdef __CUDACC_RTC__  /* compiled at run time for a user-defined cluster type (NVRTC has no host headers) */
+typedef unsigned char uint8_t;
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #define PMDI_MAX_K 8
 #define PMDI_MAX_N 256
@@ -23,13 +31,18 @@
 #define PMDI_WF 64  /* features per warp iteration: 32 lanes x one 128-bit load */
 #define PMDI_NT 512 /* threads per CTA of the sweep kernel */
 
-enum { T_GAUSSIAN = 0, T_CATEGORICAL = 1, T_NEGBINOM = 2 };
+enum { T_GAUSSIAN = 0, T_CATEGORICAL = 1, T_NEGBINOM = 2, T_USER = 3 /* registered device functor */ };
 enum { DRAW_ALLOC = 0, DRAW_RESAMP = 1, DRAW_SHUFFLE = 2, DRAW_SELECT = 3, DRAW_FEATURE = 4 };
+
+/* bytes per staged observation element: doubles for Gaussian data and for user types on Float64 data */
+#define PMDI_XBYTES(ds_) (((ds_).type == T_GAUSSIAN || ((ds_).type == T_USER && (ds_).uW > 0)) ? 8u : 4u)
 
 struct DsDev {
   int type, D, Dp, J;
   int Lmax, all_on, x_off /* byte offset of this dataset's row in the smem staging area */, nflag;
-  int FB, pad0;         /* features per block (one warp's share of a row; aux and J are per block): 256, spec engine 128 */
+  int FB, uW;           /* features per block (one warp's share of a row; aux and J are per block): 256, spec engine 128;
+                           user type: doubles of state per feature                                */
+  double* ust;          /* user type: state [row][uW][Dp]                                          */
   const void* x;        /* [n_obs][Dp]: f64 (Gaussian) or i32 (others), row-major        */
   const void* xstage;   /* what the sweep stages: x, or x with the feature flags folded in */
   const uint8_t* flag;  /* [Dp], padded features are 0                                    */

@@ -161,13 +161,13 @@ __device__ __noinline__ void pool_issue_obs(const SweepParams& sp, int step, uns
   const int obs = sp.order[sp.n1 - 1 + step];
   unsigned total = 0;
 #pragma unroll 1
-  for (int k = 0; k < sp.K; ++k) total += (unsigned)sp.ds[k].Dp * (sp.ds[k].type == T_GAUSSIAN ? 8u : 4u);
+  for (int k = 0; k < sp.K; ++k) total += (unsigned)sp.ds[k].Dp * PMDI_XBYTES(sp.ds[k]);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // earlier generic reads of the slot
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(total) : "memory");
 #pragma unroll 1
   for (int k = 0; k < sp.K; ++k) {
     const DsDev& ds = sp.ds[k];
-    const unsigned bytes = (unsigned)ds.Dp * (ds.type == T_GAUSSIAN ? 8u : 4u);
+    const unsigned bytes = (unsigned)ds.Dp * PMDI_XBYTES(ds);
     const unsigned char* src = (const unsigned char*)ds.xstage + (size_t)obs * bytes;
     const unsigned dst = (unsigned)__cvta_generic_to_shared(xring + (size_t)b * sp.sm_x_bytes + ds.x_off);
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -250,6 +250,12 @@ __device__ __noinline__ void pool_eval_rows(const SweepParams& sp, PoolSmem& sm,
             v = nb_block(ds.S + (long long)c * ds.Dp + fo, (long long)(d - c) * ds.Dp, ds.aux + (long long)c * ds.J + j,
                          ds.aux + (long long)d * ds.J + j, nit, mode, nc, xp + xo + fo * 4u, xc + xo + fo * 4u,
                          (unsigned)__cvta_generic_to_shared(T.lf), sp.lf_T, &vs);
+#ifdef PMDI_USER_STRUCT
+          } else if (ds.type == T_USER) {
+            const unsigned eb = ds.uW < 0 ? 4u : 8u;
+            v = user_block(ds, ds.ust + (long long)c * PmdiUser::WORDS * ds.Dp + fo, (long long)(d - c) * PmdiUser::WORDS * ds.Dp,
+                           ds.flag + fo, nit, mode, nc, xp + xo + fo * eb, xc + xo + fo * eb, &vs);
+#endif
           } else {
             v = cat_block(pd.cw + ((long long)c * ds.Dp + fo) * pd.wpf, (long long)(d - c) * ds.Dp * pd.wpf, pd.wpf,
                           pd.fpw, nit, mode, xp + xo + fo * 4u, xc + xo + fo * 4u, &vs);
@@ -990,7 +996,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_pool_dbg(const 
 // ------------------------------------------------------------------------------------------------
 
 // all rows of a dataset's packed categorical counts to zero (the other statistics: k_init_rows)
-__global__ void k_pool_init_rows(PoolDev pd, long long words) {
+extern "C" __global__ void k_pool_init_rows(PoolDev pd, long long words) {
   const long long stride = (long long)gridDim.x * blockDim.x;
 #pragma unroll 1
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) pd.cw[i] = 0ull;
@@ -999,7 +1005,7 @@ __global__ void k_pool_init_rows(PoolDev pd, long long words) {
 // Start of a sweep: the rho-prefix clusters (rows 0..N-1, built by k_prefix_build / k_proto_aux) are
 // shared by all particles (src/pmdi.jl:197-199: particle[u,:,k] .= id; clusters_counts = particles).
 // One block per dataset.
-__global__ void k_pool_init(SweepParams sp) {
+extern "C" __global__ void k_pool_init(SweepParams sp) {
   const int k = blockIdx.x, t = threadIdx.x, NT = blockDim.x, N = sp.N, Ps = sp.Ps;
   const PoolDev pd = sp.pd[k];
   const DsDev& ds = sp.ds[k];
@@ -1035,7 +1041,7 @@ __global__ void k_pool_init(SweepParams sp) {
 
 // packed categorical counts of the prefix prototypes from the member lists (rows 0..N-1):
 // grid (ceil(Dp/128), N), thread per feature
-__global__ void k_pool_prefix_cat(SweepParams sp, int k, const int* members, const int* off) {
+extern "C" __global__ void k_pool_prefix_cat(SweepParams sp, int k, const int* members, const int* off) {
   const int m = blockIdx.y, q = blockIdx.x * blockDim.x + threadIdx.x;
   const DsDev& ds = sp.ds[k];
   const PoolDev& pd = sp.pd[k];
@@ -1059,7 +1065,7 @@ __global__ void k_pool_prefix_cat(SweepParams sp, int k, const int* members, con
 // Particle selection (src/pmdi.jl:345-350), lineage back-trace, s[:] = sstar[p_star,:,:] (:373),
 // plus the reductions the host's update_hypers reads (src/update_hypers.jl:72,109-115): label counts
 // per (label, dataset) and, per dataset pair, the number of observations with equal labels.
-__global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long long* p_star_out,
+extern "C" __global__ void k_finish_pool(SweepParams sp, int compat, long long* s_out, long long* p_star_out,
                               long long* cluster_n, int* cur_at, long long* label_counts, long long* pair_agree,
                               long long* contingency) {
   const int t = threadIdx.x, NT = blockDim.x, P = sp.P, K = sp.K, N = sp.N;

@@ -13,6 +13,7 @@
 // predictive (same forms as cluster_types.cuh).
 #pragma once
 #include "cluster_types.cuh"
+#include "user_type.cuh"
 
 // ------------------------------------------------------------------------------------------
 // Gaussian.  Pointers are at this lane's first feature of the block; n = size of the SOURCE row.

@@ -1119,7 +1119,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep_spec_dbg(const 
 // Start of a sweep: the rho-prefix clusters (rows 0..N-1) are shared by all particles
 // (src/pmdi.jl:197-199); the live ones open the list of live rows; every other row is free.
 // One block per dataset.
-__global__ void k_spec_init(SweepParams sp) {
+extern "C" __global__ void k_spec_init(SweepParams sp) {
   const int k = blockIdx.x, t = threadIdx.x, NT = blockDim.x, N = sp.N, Ps = sp.Ps;
   const PoolDev pd = sp.pd[k];
   const DsDev& ds = sp.ds[k];

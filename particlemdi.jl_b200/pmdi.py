@@ -46,6 +46,16 @@ class NegBinomCluster:
     tag = NEGBINOM
 
 
+class UserCluster:
+    """A user-defined cluster type (the reference's plugin contract, README.md:48-88): CUDA source of a struct with
+    init / logprob / add / logmarginal (include/pmdi_cuda.h, pmdi_register_cluster_type), compiled for the device
+    when a run first uses it.  ``integer_data``: the type is bound to Int64 data (counts, levels)."""
+
+    def __init__(self, name, cuda_src, struct_name=None, integer_data=False):
+        self.name = name
+        self.tag = capi.register_cluster_type(name, cuda_src, struct_name or name, capi.I64 if integer_data else capi.F64)
+
+
 def _tag(t):
     if isinstance(t, (int, np.integer)):
         return int(t)
