@@ -85,6 +85,9 @@ struct SpecTables {
 };
 
 #define STRACE(step_, tag_) if constexpr (DBG) spec_trace(sp, sm, (step_), (tag_));
+// bounds checks of the instrumented kernel instantiation (every debug-capture sweep of the parity tests runs them):
+// a row id outside its pool, a list longer than its storage or an id handed out twice ends the sweep with error 90+
+#define SCHECK(cond_, code_) if constexpr (DBG) { if (!(cond_)) { atomicExch(sp.err, (code_)); sm.fail = 1; } }
 __device__ __forceinline__ void spec_trace(const SweepParams& sp, SpecSmem& sm, int step, unsigned tag) {
   if (sp.trace && step == sp.trace_step && (int)blockIdx.x == sp.trace_cta && (threadIdx.x & 31) == 0) {
     const int w = threadIdx.x >> 5;
@@ -553,7 +556,8 @@ __device__ __noinline__ void spec_fix(const SweepParams& sp, SpecSmem& sm, const
     if (i < n_old) {
       const int4 en = spec_entry(sp, T, e, lo, i);
       const int k = (unsigned)en.x >> SPEC_KSHIFT, v = en.x & SPEC_VMASK, c = en.y, n = en.z;
-      const PoolDev& pd = sp.pd[k];
+      SCHECK(k < K && v < sp.pd[k < K ? k : 0].cap - 1 && c >= 0 && c < sp.pd[k < K ? k : 0].cap - 1, 94)
+      const PoolDev& pd = sp.pd[k < K ? k : 0];
       const int tot = ldcg_i32(pd.chosen + (size_t)b3 * pd.cap + v);
       const int rf = ldcg_i32(pd.refcnt + (size_t)par1 * pd.cap + v);
       const int cv = ldcg_info(pd.info + (size_t)parn * pd.cap + v).z;
@@ -612,6 +616,7 @@ __device__ __noinline__ void spec_fix(const SweepParams& sp, SpecSmem& sm, const
     }
   }
   __syncthreads();
+  SCHECK((long long)nb <= sp.lcap, 93)
   if (tid == 0) { sm.cnt = nb; sm.lpar = ln; }
   __syncthreads();
 }
@@ -635,7 +640,7 @@ __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, cons
 #pragma unroll 1
   for (int j0 = e; j0 < total; j0 += GE * rpc, buf ^= 1) {
     const int j = j0 + sub * GE;
-    const bool active = sub < rpc && j < total;
+    bool active = sub < rpc && j < total;
     int k = 0, v = 0, c = 0, nc = 0;
     double rcv = 0.0;
     if (active) {
@@ -647,7 +652,9 @@ __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, cons
       }
       const DsDev& ds = sp.ds[k];
       const PoolDev& pd = sp.pd[k];
-      if (wj < ds.J) {
+      SCHECK(k >= 0 && k < K && v >= 0 && v < pd.cap && (mode == 0 || (c >= 0 && c < pd.cap - 1 && c != v)) && nc >= 0 && nc <= sp.n_obs, 91)
+      if (sm.fail) { active = false; }
+      if (active && wj < ds.J) {
         if (obs_ok < st) {  // x[st] has landed in the ring (x[st-1] was waited for one step ago)
           if (lane == 0) {
 #pragma unroll 1
@@ -700,6 +707,7 @@ __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, cons
 #pragma unroll 1
         for (int jb = 0; jb < ds.J; ++jb) lv += sm.red[buf][lane][r0 + jb];
         id = spec_pop_id(sp, sm, T, k);  // the id of the next child; its cluster size is known now
+        SCHECK(id >= 0 && id < pd.cap - 1 && id != v && id != c, 92)
         __stcg(ds.n + id, nc + 2 - lane);
       }
       // the row of the empty cluster also carries the id handed to its child's child (read by the next fix)

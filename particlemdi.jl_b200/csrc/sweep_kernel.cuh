@@ -292,7 +292,7 @@ __device__ __noinline__ bool bar_wait(const SweepParams& sp, unsigned long long 
   while (ld_counter(sp) < target) {
     if (((++spins) & 0x3ffu) == 0) {
       if (__ldcg(sp.err) != 0) return false;
-      if (globaltimer_ns() - t0 > 4000000000ull) { atomicExch(sp.err, 77); return false; }
+      if (globaltimer_ns() - t0 > sp.wd_ns) { atomicExch(sp.err, 77); return false; }
     }
   }
   if (sp.R > 1) __threadfence_system(); else __threadfence();
@@ -521,7 +521,7 @@ __device__ __noinline__ int check_resolved(const SweepParams& sp, SweepSmem& sm,
     const int rs = ld_vol(&sm.res_step);
     if (rs >= s) r = ld_vol(&sm.res_flag) ? 2 : 1;
     else if (rs == s - 1 && ld_vol(&sm.arrived) >= s &&
-             ld_counter(sp) >= sm.q[s & 1].ep &&
+             ld_counter(sp) >= *(volatile unsigned long long*)&sm.q[s & 1].ep &&  // after `arrived`: never a stale epoch
              atomicCAS(&sm.res_claim, s - 1, s) == s - 1) r = 3;
   }
   r = __shfl_sync(FULL, r, 0);
@@ -853,7 +853,7 @@ extern "C" __global__ void __launch_bounds__(PMDI_NT, 1) k_sweep(const __grid_co
           const unsigned long long now = globaltimer_ns();
           if (idle_t0 == 0) idle_t0 = now;
           if (__ldcg(sp.err) != 0) st_vol(&sm.fail, 1);
-          else if (now - idle_t0 > 4000000000ull) { atomicExch(sp.err, 79); st_vol(&sm.fail, 1); }
+          else if (now - idle_t0 > sp.wd_ns) { atomicExch(sp.err, 79); st_vol(&sm.fail, 1); }
         }
         if (ld_vol(&sm.fail)) what = 4;
         else if (ld_vol(&sm.res_flag) && t == ld_vol(&sm.res_step) + 2) what = 3;

@@ -426,10 +426,12 @@ def posterior_similarity(alloc):
 # ------------------------------------------------------------------ the entry point
 def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, featureSelect=None,
          dataNames=None, seed=0, device=0, stale_gamma_table=False, sstar_compat=False, factorised=None,
-         device_reductions=True):
+         device_reductions=True, reference_literal=False, distributed=False):
     """``pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile; thin, featureSelect,
     dataNames)`` of src/pmdi.jl:36-40.  Side effect: the CSV file(s); returns a small dict of
     timings and counters (the reference returns nothing)."""
+    if reference_literal:  # the literal reference in one switch: never-refreshed gamma table, trajectories not permuted
+        stale_gamma_table, sstar_compat, factorised = True, True, False
     K = len(dataFiles)
     n_obs = int(dataFiles[0].shape[0])
     if dataNames is None:
@@ -468,7 +470,20 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
     v = update_v(n_obs, Z, rng)                                   # :96
 
     counts = agree = None  # first iteration: counted from the initial allocation
-    ctx = capi.Context(dataFiles, types, N, particles, device=device)  # raises without a GPU
+    # distributed: one process per GPU of a node (torch.distributed initialised by the caller), the particles sharded
+    # over the ranks; every rank runs this same loop with the same seed (identical hyper-parameters everywhere),
+    # rank 0 writes the files
+    rank, world = 0, 1
+    if distributed:
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+    ctx = capi.Context(dataFiles, types, N, particles, device=device, rank=rank, n_ranks=world)  # raises without a GPU
+    if world > 1:
+        ctx.connect()
+    if rank != 0:
+        outputFile, featureSelect_file = "/dev/null", ("/dev/null" if featureSelect is not None else None)
+    else:
+        featureSelect_file = featureSelect
     stats_out = dict(sweep_device_ms=0.0, n_resamples=0, iterations=0)
     ffile = None
     try:
@@ -476,7 +491,7 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
         if featureSelect is not None:                             # :106-128
             flags = [rng.random(d.shape[1]) < 0.5 for d in dataFiles]
             names = [f"{dataNames[k]}_d{d + 1}" for k in range(K) for d in range(dataFiles[k].shape[1])]
-            ffile = open(featureSelect, "w")
+            ffile = open(featureSelect_file, "w")
             ffile.write(",".join(names) + "\n")
             ffile.write(",".join("true" if f else "false" for fl in flags for f in fl) + "\n")
             for k in range(K):
@@ -499,9 +514,10 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
                     update_phi(phi, v, s, tables, rng, agree_all=agree, gamma=gamma)  # :181-183
                 Z = update_Z(phi, tables, gamma)                  # :184
                 v = update_v(n_obs, Z, rng)                       # :185
-                r = ctx.sweep(s, order_obs, n1, Pi, phi if K > 1 else None,
-                              logweight_init=0.0 if it == 1 else 1.0,   # :99, :372
-                              seed=seed, it=it, sstar_compat=sstar_compat)  # :188-350, :373
+                do_sweep = ctx.sweep_sharded if world > 1 else ctx.sweep
+                r = do_sweep(s, order_obs, n1, Pi, phi if K > 1 else None,
+                             logweight_init=0.0 if it == 1 else 1.0,   # :99, :372
+                             seed=seed, it=it, sstar_compat=sstar_compat)  # :188-350, :373
                 s = np.array(r["s"], dtype=np.int64, order="C")
                 stats_out["sweep_device_ms"] += r["device_ms"]
                 stats_out["n_resamples"] += r["n_resamples"]

@@ -43,3 +43,21 @@ def run_rank(rank, world, port, case_kw, seed, outdir, use_tapes, sweeps):
         ctx.close()
     finally:
         dist.destroy_process_group()
+
+
+def run_pmdi_rank(rank, world, port, outdir, iters):
+    """pmdi() with the particles sharded over `world` GPUs: every rank runs the host loop, rank 0 writes the CSV."""
+    import torch
+    import torch.distributed as dist
+    import pmdi_b200  # noqa: F401
+    from pmdi_b200 import pmdi as host
+    from test_gpu_pmdi import _separable
+    torch.cuda.set_device(rank)
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        data, _ = _separable(70, seed=5)
+        host.pmdi(data, [0, 2, 1], 6, 24, 0.25, iters, os.path.join(outdir, f"sharded_rank{rank}.csv"), seed=3,
+                  device=rank, distributed=True)
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()

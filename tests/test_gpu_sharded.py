@@ -82,3 +82,23 @@ def test_sharded_sweep_matches_oracle(name, world, tmp_path):
     if name in MOVES:
         assert moved > 0    # resampling did duplicate particles ...
         assert remote > 0   # ... and some of their rows were pulled from another rank's GPU
+
+
+def test_pmdi_sharded_over_two_gpus_equals_one_gpu(tmp_path):
+    """The reference-facing entry point with the particles sharded over two GPUs writes the same allocations as on
+    one GPU (the sharded sweep reproduces the global particle set bit for bit, the host loop is the same)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    import pmdi_b200  # noqa: F401
+    from pmdi_b200 import pmdi as host
+    from sharded_worker import run_pmdi_rank
+    from test_gpu_pmdi import _separable
+    iters = 8
+    mp.spawn(run_pmdi_rank, args=(2, _free_port(), str(tmp_path), iters), nprocs=2, join=True)
+    data, _ = _separable(70, seed=5)
+    one = tmp_path / "one.csv"
+    host.pmdi(data, [0, 2, 1], 6, 24, 0.25, iters, str(one), seed=3)
+    a = host.read_allocations(str(tmp_path / "sharded_rank0.csv"), 3, 70)
+    b = host.read_allocations(str(one), 3, 70)
+    np.testing.assert_array_equal(a, b)
