@@ -535,11 +535,13 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
 // anc[0] == 1).  The Fisher-Yates shuffle followed by partstar[1]=1 and sort! only decides WHICH
 // element of the sorted systematic sample the reference particle replaces: the one the shuffle
 // moves to position 1; that index is traced through the swaps without moving anything.
-__device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step, int ev, double mx, int* s_tmp) {
+__device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step, int ev, double mx, int* s_tmp,
+                                                const double* lw = nullptr) {
+  if (!lw) lw = sp.lw;  // (the spec engine keeps two copies of the log-weights, by step parity)
   const int P = sp.P, t = threadIdx.x;
 #pragma unroll 1
   for (int p = t; p < P; p += PMDI_NT) {
-    sp.sc_w[p] = pm_exp(__ldcg(on_rank(sp, sp.lw + p, p / sp.Ps)) - mx);  // the holder's copy (NVLink when remote)
+    sp.sc_w[p] = pm_exp(__ldcg(on_rank(sp, lw + p, p / sp.Ps)) - mx);  // the holder's copy (NVLink when remote)
     const double us = sp.tape_shuffle ? sp.tape_shuffle[(size_t)step * P + p]
                                       : pm_uniform(sp.seed, sp.iter, DRAW_SHUFFLE, step, 0, p);
     int jj = 1 + (int)floor(us * (double)(p + 1));

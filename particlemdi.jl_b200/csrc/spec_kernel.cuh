@@ -76,6 +76,8 @@ struct SpecTables {
   int* u_occ;      // [MU] occupied labels of the unit
   int* u_c1;       // [MU] row chosen one step ago
   int* u_c2;       // [MU] row chosen two steps ago (its choice counter is cleared now)
+  int* u_prow;     // [MU] the row the chosen label pointed at before this step's commit (undo)
+  double* lw_prev; // [MS] the particles' log-weights before this step's commit (undo)
   int* u_ks;       // [MU] dataset | local slot << 8
   int* rm_s;       // [MU][N]
   // E-CTAs
@@ -260,6 +262,7 @@ __device__ __noinline__ void spec_commit(const SweepParams& sp, SpecSmem& sm, co
     const int c2 = T.u_c2[u];
     if (c2 >= 0) __stcg(pd.chosen + (size_t)z3 * pd.cap + c2, 0);
     T.u_c2[u] = T.u_c1[u]; T.u_c1[u] = c;
+    T.u_prow[u] = c;
     T.rm_s[u * N + label] = child;
     __stcg(pd.rowmap + ((size_t)(sm.ev & 1) * sp.Ps + slot) * N + label, child);
 #pragma unroll 1
@@ -274,6 +277,7 @@ __device__ __noinline__ void spec_commit(const SweepParams& sp, SpecSmem& sm, co
       const volatile double* iv = T.inc_s + (size_t)sl * K;
       const volatile int* lv = T.lab_s + (size_t)sl * K;
       double w = T.lw_s[sl];
+      T.lw_prev[sl] = w;
 #pragma unroll 1
       for (int kk = 0; kk < K; ++kk) w += iv[kk];  // dataset order, as src/pmdi.jl:210,233
       int idx = 0;
@@ -285,7 +289,8 @@ __device__ __noinline__ void spec_commit(const SweepParams& sp, SpecSmem& sm, co
           ++idx;
         }
       T.lw_s[sl] = w;
-      __stcg(sp.lw + p, w);
+      __stcg(sp.lw + (size_t)(step & 1) * P + p, w);  // two copies by step parity: the decision on step t is taken
+                                                      // while step t+1 is already being committed
       if (DBG && sp.dbg_lw) sp.dbg_lw[(size_t)step * P + p] = w;
     }
   }
@@ -301,6 +306,7 @@ __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, in
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, P = sp.P;
   // (with several ranks: this rank's particles; the ranks' partials are exchanged below)
   const int per = (sp.Ps + POOL_NW - 1) / POOL_NW, p_lo = sp.slot0 + warp * per, p_hi = min(sp.slot0 + sp.Ps, p_lo + per);
+  const double* lw = sp.lw + (size_t)(t & 1) * P;
   double mxv = -INFINITY;
 #pragma unroll 1
   for (int p0 = p_lo; p0 < p_hi; p0 += 256) {
@@ -308,7 +314,7 @@ __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int p = p0 + lane + 32 * i;
-      v[i] = p < p_hi ? ldcg_f64(sp.lw + p) : -INFINITY;
+      v[i] = p < p_hi ? ldcg_f64(lw + p) : -INFINITY;
     }
 #pragma unroll
     for (int i = 0; i < 8; ++i) mxv = fmax(mxv, v[i]);
@@ -321,7 +327,7 @@ __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, in
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int p = p0 + lane + 32 * i;
-      v[i] = p < p_hi ? ldcg_f64(sp.lw + p) : -INFINITY;
+      v[i] = p < p_hi ? ldcg_f64(lw + p) : -INFINITY;
     }
 #pragma unroll 1
     for (int i = 0; i < 8; ++i) {
@@ -792,7 +798,8 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
   const bool has_next = st + 1 < sp.steps;
   // every E-CTA (of every rank) has finished E'(st+2), every commit of step st is in
   if (!spec_xsync(sp, sm)) return false;
-  if ((int)blockIdx.x == sp.G - 1) pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp);  // the D-CTA knows the maximum
+  if ((int)blockIdx.x == sp.G - 1)  // the D-CTA knows the maximum
+    pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp, sp.lw + (size_t)(st & 1) * sp.P);
   if (!spec_gsync(sp, sm)) return false;
   const int* anc = sp.anc_log + (size_t)ev * sp.P;
   if (gt == (long long)sp.GP * PMDI_NT && has_next)  // rows counted for step st+1 that this decision may kill
@@ -963,7 +970,8 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
   T.Pi_s = T.lp_s + (size_t)NW * Npad;
   T.lw_s = T.Pi_s + (size_t)K * N;
   T.inc_s = T.lw_s + MS;
-  T.ch_s = (int*)(T.inc_s + MU);
+  T.lw_prev = T.inc_s + MU;
+  T.ch_s = (int*)(T.lw_prev + MS);
   T.lab_s = T.ch_s + (size_t)NW * Npad;
   T.pcount = T.lab_s + MU;
   T.u_c = T.pcount + MS;
@@ -971,7 +979,8 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
   T.u_occ = T.u_child + MU;
   T.u_c1 = T.u_occ + MU;
   T.u_c2 = T.u_c1 + MU;
-  T.u_ks = T.u_c2 + MU;
+  T.u_prow = T.u_c2 + MU;
+  T.u_ks = T.u_prow + MU;
   T.rm_s = T.u_ks + MU;
   T.el_s = (int4*)rt;  // the two roles overlay the same region
   T.fc_s = (int*)(T.el_s + (size_t)2 * SPEC_EC);
@@ -1035,20 +1044,34 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
       // ---- P(t): proposals (read-only), the decision on the resampling after step t-1, commit
 #pragma unroll 1
       for (int u = warp; u < nu; u += NW) spec_propose<DBG>(sp, sm, T, u, t);
-      if (t > 0) {
-        __syncthreads();
-        if (!spec_wait_decision(sp, sm, t - 1)) return;
-        if (sm.res_flag) {  // the same in every CTA: drop the proposals, resample, propose again
-          if (!spec_resample(sp, sm, T, ns, t - 1, s_tmp, true, e)) return;
-          PHASE_MARK(6)
-#pragma unroll 1
-          for (int u = warp; u < nu; u += NW) spec_propose<DBG>(sp, sm, T, u, t);
-        }
-      }
       STRACE(t, 49)
 #pragma unroll 1
       for (int u = warp; u < nu; u += NW) spec_commit<DBG>(sp, sm, T, u, t, ns);
       PHASE_MARK(2)
+      if (t > 0) {
+        // The step was committed without knowing whether step t-1 ends in a resampling: the decision (an exchange
+        // over NVLink when the particles are sharded) had the whole of this phase to arrive.  When it says
+        // "resample" (a few steps per sweep) the commit is undone, the particles are resampled, the step is redone.
+        __syncthreads();
+        if (!spec_wait_decision(sp, sm, t - 1)) return;
+        if (sm.res_flag) {
+#pragma unroll 1
+          for (int u = tid; u < nu; u += PMDI_NT) {  // labels back to the rows they pointed at; weights back
+            const int ks = T.u_ks[u], k = ks & 0xff, slot = cta + (ks >> 8) * GP, label = T.lab_s[u];
+            T.rm_s[u * N + label] = T.u_prow[u];
+            __stcg(sp.pd[k].rowmap + ((size_t)(sm.ev & 1) * sp.Ps + slot) * N + label, T.u_prow[u]);
+            atomicSub(&sm.rows_ref[k], (unsigned)T.u_occ[u]);
+          }
+#pragma unroll 1
+          for (int sl = tid; sl < ns; sl += PMDI_NT) T.lw_s[sl] = T.lw_prev[sl];
+          if (!spec_resample(sp, sm, T, ns, t - 1, s_tmp, true, e)) return;
+          PHASE_MARK(6)
+#pragma unroll 1
+          for (int u = warp; u < nu; u += NW) spec_propose<DBG>(sp, sm, T, u, t);
+#pragma unroll 1
+          for (int u = warp; u < nu; u += NW) spec_commit<DBG>(sp, sm, T, u, t, ns);
+        }
+      }
     } else if (is_d) {
       if (t > 0) {
         spec_decide(sp, sm, t - 1);
@@ -1093,7 +1116,7 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
   }
   if (cta == 0)  // after a final resampling all log-weights are 1.0 (src/pmdi.jl:319)
     for (int p = tid; p < sp.P; p += PMDI_NT)
-      sp.lw_out[p] = final_res ? 1.0 : __ldcg(on_rank(sp, sp.lw + p, p / sp.Ps));
+      sp.lw_out[p] = final_res ? 1.0 : __ldcg(on_rank(sp, sp.lw + (size_t)((steps - 1) & 1) * sp.P + p, p / sp.Ps));
   if (timing && tid < 8) sp.phase_ns[(size_t)cta * 8 + tid] = sm.tacc[tid] / NW;
   if (cta == 0 && tid == 0) sp.counters[2] = sm.ev;
   // the peers' stores into this rank's allocation log have landed before the finish kernel reads it
