@@ -117,6 +117,7 @@ struct __attribute__((aligned(16))) SweepParams {
   long long proto_base;   /* first row of the rho-prefix prototypes (dense: Ps*N, pool: 0)   */
   unsigned long long wd_ns; /* watchdog of the in-kernel waits                               */
   int4* pull_jobs;        /* resampling: (dataset, source rank, source row, local row) of rows to pull */
+  int* pull_map;          /* spec engine, several ranks: [K][R][cap] local copy of a remote row during a resampling (-1: none) */
   double* rank_part;      /* [2][R][4] per step parity and rank: max, sum w, sum w^2, step tag */
   unsigned long long* rows_ref; /* [K] occupied (particle, label) rows referenced by proposals */
   const double* Pi;      /* [K][N]                                          */

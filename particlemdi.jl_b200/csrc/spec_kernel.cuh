@@ -796,11 +796,16 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
   const int parn = (st + 1) & 1;  // info of step st+1: lp and child ids of everything that may be live;
                                   // also the copy of the reference counts the fix of step st+1 will read
   const bool has_next = st + 1 < sp.steps;
+  // sub-phase timers (instrumented runs): tacc[4] wait for all CTAs + plan, [5] row maps + pulls, [7] recount + rebuild
+  const bool tm = sp.phase_ns != nullptr && threadIdx.x == 0;
+  unsigned long long t_ = tm ? globaltimer_ns() : 0ull;
+#define RS_MARK(i_) if (tm) { const unsigned long long n_ = globaltimer_ns(); sm.tacc[i_] += (n_ - t_) * POOL_NW; t_ = n_; }
   // every E-CTA (of every rank) has finished E'(st+2), every commit of step st is in
   if (!spec_xsync(sp, sm)) return false;
   if ((int)blockIdx.x == sp.G - 1)  // the D-CTA knows the maximum
     pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp, sp.lw + (size_t)(st & 1) * sp.P);
   if (!spec_gsync(sp, sm)) return false;
+  RS_MARK(4)
   const int* anc = sp.anc_log + (size_t)ev * sp.P;
   if (gt == (long long)sp.GP * PMDI_NT && has_next)  // rows counted for step st+1 that this decision may kill
     atomicAdd((unsigned long long*)&sp.counters[4], (unsigned long long)sm.cnt);
@@ -819,31 +824,57 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
       } else if (slot == 0 || ldcg_i32(anc + sp.slot0 + slot - 1) != a + 1) {
         // first local child of an ancestor held by another rank: its occupied rows are pulled into four
         // fresh local rows each (the row, its child of step st+1, the two ids handed out for step st+2)
+        // A remote row is pulled ONCE however many ancestors over there refer to it (particles that share a
+        // cluster on their rank share its copy here): the first to claim it in pull_map reserves the ids.
         const int rb = ldcg_i32(on_rank(sp, rm_old, ra) + (size_t)la * N + m);
-        int d = pd.cap - 1;
         if (rb != pd.cap - 1) {
-          const int first = spec_gclaim(pd, 4);
-          if (first < 0) { atomicExch(sp.err, 80); sm.fail = 1; }
-          else {
-            const int v2 = spec_gtake(pd, first), c2 = spec_gtake(pd, first + 1);
-            const int a2 = spec_gtake(pd, first + 2), b2 = spec_gtake(pd, first + 3);
-            const long long job = atomicAdd((unsigned long long*)&sp.counters[5], 1ull);
-            sp.pull_jobs[2 * job] = make_int4(k | (ra << 8), rb, v2, c2);
-            sp.pull_jobs[2 * job + 1] = make_int4(a2, b2, 0, 0);
-            d = v2;
+          int* pm = sp.pull_map + ((size_t)k * sp.R + ra) * pd.cap + rb;
+          if (atomicCAS(pm, -1, -2) == -1) {
+            // (nobody pushes to the free stack during a resampling: one atomic claims the four slots)
+            const int first = atomicSub(pd.ctr + 1, 4) - 4;
+            if (first < 0) { atomicExch(sp.err, 80); sm.fail = 1; }
+            else {
+              const int v2 = spec_gtake(pd, first), c2 = spec_gtake(pd, first + 1);
+              const int a2 = spec_gtake(pd, first + 2), b2 = spec_gtake(pd, first + 3);
+              const long long job = atomicAdd((unsigned long long*)&sp.counters[5], 1ull);
+              sp.pull_jobs[2 * job] = make_int4(k | (ra << 8), rb, v2, c2);
+              sp.pull_jobs[2 * job + 1] = make_int4(a2, b2, 0, 0);
+              __stcg(pm, v2);
+            }
           }
         }
-        __stcg(rm_new + i, d);
       }
     }
   }
   if (sp.R > 1) {
     if (!spec_gsync(sp, sm)) return false;
+    // every label of a first child of a remote ancestor: the local copy of the row it referred to over there
+#pragma unroll 1
+    for (int k = 0; k < K; ++k) {
+      const PoolDev& pd = sp.pd[k];
+      const int* rm_old = pd.rowmap + (size_t)(ev & 1) * Ps * N;
+      int* rm_new = pd.rowmap + (size_t)((ev + 1) & 1) * Ps * N;
+#pragma unroll 1
+      for (long long i = gt; i < (long long)Ps * N; i += GT) {
+        const int slot = (int)(i / N), m = (int)(i - (long long)slot * N);
+        const int a = ldcg_i32(anc + sp.slot0 + slot) - 1;
+        const int ra = a / Ps, la = a - ra * Ps;
+        if (ra == sp.rank || !(slot == 0 || ldcg_i32(anc + sp.slot0 + slot - 1) != a + 1)) continue;
+        const int rb = ldcg_i32(on_rank(sp, rm_old, ra) + (size_t)la * N + m);
+        __stcg(rm_new + i, rb == pd.cap - 1 ? rb : ldcg_i32(sp.pull_map + ((size_t)k * sp.R + ra) * pd.cap + rb));
+      }
+    }
+    if (!spec_gsync(sp, sm)) return false;
     // pull the reserved rows (a warp per row); the other children of a remote ancestor share its first child's map
     const long long njobs = __ldcg(&sp.counters[5]);
     const long long gw = gt >> 5, GWp = GT >> 5;
 #pragma unroll 1
-    for (long long job = gw; job < njobs; job += GWp) spec_row_pull(sp, __ldcg(sp.pull_jobs + 2 * job), __ldcg(sp.pull_jobs + 2 * job + 1), parn);
+    for (long long job = gw; job < njobs; job += GWp) {
+      const int4 j0 = __ldcg(sp.pull_jobs + 2 * job);
+      spec_row_pull(sp, j0, __ldcg(sp.pull_jobs + 2 * job + 1), parn);
+      if ((threadIdx.x & 31) == 0)  // the map is clear again for the next resampling
+        __stcg(sp.pull_map + ((size_t)(j0.x & 0xff) * sp.R + (j0.x >> 8)) * sp.pd[j0.x & 0xff].cap + j0.y, -1);
+    }
     if (gt == 0) sp.counters[3] += njobs;
 #pragma unroll 1
     for (int k = 0; k < K; ++k) {
@@ -861,6 +892,7 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
     if (!spec_gsync(sp, sm)) return false;
     if (gt == 0) sp.counters[5] = 0;
   }
+  RS_MARK(5)
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
     const PoolDev& pd = sp.pd[k];
@@ -931,6 +963,8 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
     }
   }
   if (!spec_xsync(sp, sm)) return false;  // no rank recycles a row while a peer may still be pulling it
+  RS_MARK(7)
+#undef RS_MARK
   if (gt == 0 && has_next) atomicAdd((unsigned long long*)&sp.counters[4], (unsigned long long)(-(long long)ldcg_i32(sp.gcnt)));
   if (threadIdx.x == 0) { sm.ev = ev + 1; sm.res_flag = 0; }
   __syncthreads();
