@@ -591,21 +591,22 @@ def cfg4_block(world, rank, local, stream, flush, peak, peak_src, traffic_for, s
     return out if rank == 0 else None
 
 
-def pmdi_block(local, iters=12):
+def pmdi_block(local):
     """MCMC iterations per second through pmdi() - the sweep on the GPU plus the host-side hyper-parameter
-    updates, align_labels! and the CSV writer (src/pmdi.jl:164-384) - for the configurations whose N^K
-    hyper-parameter tables fit."""
+    updates, align_labels! and the CSV writer (src/pmdi.jl:164-384).  cfg3 runs with featureSelect on
+    (calc_logmarginal!, src/pmdi.jl:354-370) and needs the factorised normalising sums (N^K = 7.3e8)."""
     from pmdi_b200 import pmdi as host
     out = {}
-    for name in ("cfg1_iris", "cfg2_multiomics"):
+    for name, iters, fs in (("cfg1_iris", 12, False), ("cfg2_multiomics", 12, False), ("cfg3_tcga", 5, True),
+                            ("cfg4_singlecell", 3, False)):
         cfg = make_workload(name)
         with tempfile.TemporaryDirectory() as td:
             t0 = time.perf_counter()
             st = host.pmdi(cfg["data"], cfg["types"], cfg["N"], cfg["P"], cfg["rho"], iters, os.path.join(td, "out.csv"),
-                           seed=1, device=local)
+                           featureSelect=os.path.join(td, "fs.csv") if fs else None, seed=1, device=local)
             dt = time.perf_counter() - t0
         out[name] = {"iterations": iters, "mcmc_iters_per_s": iters / dt, "ms_per_iteration": 1e3 * dt / iters,
-                     "sweep_device_ms_per_iteration": st["sweep_device_ms"] / iters,
+                     "sweep_device_ms_per_iteration": st["sweep_device_ms"] / iters, "feature_select": fs,
                      "note": "first iterations of a fresh chain (the expensive regime), context creation and data upload included"}
     return out
 

@@ -120,9 +120,12 @@ typedef struct pmdi_sweep_out {
   int64_t  rows_evaluated[8]; /* per dataset: cluster rows evaluated over the sweep           */
   double   device_ms;     /* device time of the whole sweep (prefix .. selection), CUDA events */
   double   sweep_kernel_ms;  /* device time of the persistent per-observation kernel alone    */
-  double   phase_ms[8];   /* with PMDI_SWEEP_TIME_PHASES, mean over CTAs: 0 prefetch + item offsets,
-                             1 predictive, 2 proposal, 3 cluster_add, 4 grid-barrier wait,
-                             5 weights + ESS, 6 resampling, 7 unused                           */
+  double   phase_ms[8];   /* with PMDI_SWEEP_TIME_PHASES: per-warp time by phase, mean over CTAs.
+                             engine 2 (spec): 0 waiting at the grid barrier, 1 row evaluations (E-CTAs),
+                               2 proposals + commits (P-CTAs), 3 outcome bookkeeping (E-CTAs), 6 resampling,
+                               4 / 5 / 7 sub-phases of the resampling (all CTAs in + plan; row maps + pulls; rebuild)
+                             engine 1 (pool): 0 wait at B1, 1 evaluations, 2 proposals, 3 resolve, 4 wait at B2, 6 resampling
+                             engine 0 (dense): 0 idle / waiting, 1 work items, 2 proposals, 6 resampling   */
   double   phase_ms_max[8]; /* same phases, maximum over CTAs                                  */
   /* debug capture, used when PMDI_SWEEP_DEBUG is set; each may be NULL */
   double*  dbg_lp;        /* [steps][K][P][N]                                                 */

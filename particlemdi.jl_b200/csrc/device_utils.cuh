@@ -88,31 +88,3 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-
-// Grid-wide barrier of a cooperative launch (all CTAs co-resident): one monotonically increasing
-// counter; `epoch` is the arrival count that completes this barrier.  A 4 s watchdog turns a lost
-// CTA into an error flag instead of a hung GPU.
-__device__ __forceinline__ bool grid_barrier(unsigned* ctr, unsigned& epoch, unsigned G, int* err) {
-  __shared__ int s_fail;
-  __syncthreads();
-  epoch += G;
-  if (threadIdx.x == 0) {
-    int fail = 0;
-    __threadfence();
-    atomicAdd(ctr, 1u);
-    if (ld_acquire_u32(ctr) < epoch) {
-      const unsigned long long t0 = globaltimer_ns();
-      unsigned spins = 0;
-      while (ld_acquire_u32(ctr) < epoch) {
-        if (((++spins) & 0x3ffu) == 0) {
-          if (__ldcg(err) != 0) { fail = 1; break; }
-          if (globaltimer_ns() - t0 > 4000000000ull) { atomicExch(err, 77); fail = 1; break; }
-        }
-      }
-    }
-    __threadfence();
-    s_fail = fail;
-  }
-  __syncthreads();
-  return s_fail == 0;
-}

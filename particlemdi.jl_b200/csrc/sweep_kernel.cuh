@@ -140,14 +140,6 @@ __device__ __noinline__ void resample_plan(const SweepParams& sp, int step, int 
   __syncthreads();
 }
 
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
 // optional per-warp event trace of one CTA and one step (PMDI_TRACE_STEP): tag << 48 | clock64
 __device__ __noinline__ void trace_mark(const SweepParams& sp, int step, unsigned tag) {
   __shared__ int tr_cnt[PMDI_NT / 32];
