@@ -80,7 +80,7 @@ def common_config(cfg, burn):
             "rho": cfg["rho"], "features": [int(d.shape[1]) for d in cfg["data"]],
             "observation_steps_per_sweep": cfg["n"] - cfg["n1"] + 1,
             "chain_state": f"settled: {burn} untimed burn-in sweeps from the random initial allocation",
-            "l2": "256 MiB buffer written between timed sweeps (L2 flush)"}
+            "l2": "GPU arm: 256 MiB buffer written between timed sweeps (L2 flush); CPU arm: not applicable"}
 
 
 class ClockSampler:
