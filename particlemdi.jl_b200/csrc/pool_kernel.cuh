@@ -549,19 +549,37 @@ __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step,
     sp.sc_j[p] = jj;
   }
   __syncthreads();
-  if (t == 0) {  // pprob = cumsum(exp.(logweight .- max)), sequential (misc.jl:29)
+  if (t == 0) {  // pprob = cumsum(exp.(logweight .- max)), sequential (misc.jl:29); loads sixteen ahead of the adds
     double acc = 0.0;
+    int p = 0;
 #pragma unroll 1
-    for (int p = 0; p < P; ++p) { acc += sp.sc_w[p]; sp.sc_pp[p] = acc; }
+    for (; p + 16 <= P; p += 16) {
+      double v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __ldcg(sp.sc_w + p + i);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) { acc += v[i]; sp.sc_pp[p + i] = acc; }
+    }
+#pragma unroll 1
+    for (; p < P; ++p) { acc += sp.sc_w[p]; sp.sc_pp[p] = acc; }
   } else if (t == 32) {  // u, u + 1/P, ... by repeated addition (misc.jl:28,35)
     const double r = sp.tape_resamp ? sp.tape_resamp[step] : pm_uniform(sp.seed, sp.iter, DRAW_RESAMP, step, 0, 0);
     double u = r / (double)P;
 #pragma unroll 1
     for (int i = 0; i < P; ++i) { sp.sc_u[i] = u; u += 1.0 / (double)P; }
   } else if (t == 64) {  // index of the pre-shuffle element that ends at position 1
-    int tt = 0;
+    int tt = 0, pos = 2;
 #pragma unroll 1
-    for (int pos = 2; pos <= P; ++pos)
+    for (; pos + 15 <= P; pos += 16) {
+      int v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = __ldcg(sp.sc_j + pos - 1 + i);
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        if (v[i] - 1 == tt) tt = pos - 1 + i;
+    }
+#pragma unroll 1
+    for (; pos <= P; ++pos)
       if (sp.sc_j[pos - 1] - 1 == tt) tt = pos - 1;
     s_tmp[0] = tt;
   }
@@ -588,13 +606,13 @@ __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step,
     if (sp.dbg_anc) sp.dbg_anc[(size_t)step * P + i] = a;
   }
   __syncthreads();
-  if (t == 0) {
-    int dup = 0;
+  int dup = 0;  // particles that duplicate their predecessor's ancestor (a statistic)
 #pragma unroll 1
-    for (int i = 1; i < P; ++i) dup += anc[i] == anc[i - 1];
+  for (int i = 1 + t; i < P; i += PMDI_NT) dup += anc[i] == anc[i - 1];
+  if (dup) atomicAdd((unsigned long long*)&sp.counters[1], (unsigned long long)dup);
+  if (t == 0) {
     sp.ev_of_step[step] = ev;
     sp.counters[0] += 1;
-    sp.counters[1] += dup;
   }
 }
 

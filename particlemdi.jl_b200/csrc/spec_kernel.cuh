@@ -363,11 +363,13 @@ __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, in
           double* q = on_rank(sp, mine, r);
           __stcg(q, mx); __stcg(q + 1, a); __stcg(q + 2, b);
         }
-        // (the release store orders this thread's stores above before the tag: no separate system fence)
+        // ONE system fence orders all the partials before all the tags (a release store per rank would pay a
+        // round trip over NVLink each: 8 ranks -> ~20 us, longer than the step the decision has to arrive in)
+        __threadfence_system();
 #pragma unroll 1
         for (int r = 0; r < sp.R; ++r) {
           unsigned long long* f = (unsigned long long*)(on_rank(sp, mine, r) + 3);
-          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sp.tag_base + (unsigned long long)(t + 1)) : "memory");
+          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sp.tag_base + (unsigned long long)(t + 1)) : "memory");
         }
       }
       const double* base = sp.rank_part + (size_t)par * sp.R * 4;

@@ -432,6 +432,7 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
     timings and counters (the reference returns nothing)."""
     if reference_literal:  # the literal reference in one switch: never-refreshed gamma table, trajectories not permuted
         stale_gamma_table, sstar_compat, factorised = True, True, False
+    t_entry = time.perf_counter()
     K = len(dataFiles)
     n_obs = int(dataFiles[0].shape[0])
     if dataNames is None:
@@ -500,6 +501,7 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
         with open(outputFile, "w") as out:
             out.write(csv_header(K, n_obs, dataNames) + "\n")     # :147-154
             t0 = time.perf_counter()
+            stats_out["setup_s"] = t0 - t_entry   # data to the device, pool allocation (and a user type's compilation)
             out.write(csv_row(M, phi, 0, s) + "\n")               # :158
             for it in range(1, iter + 1):                         # :164
                 order_obs = rng.permutation(n_obs) + 1            # :172
@@ -541,6 +543,7 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
                     if ffile is not None:
                         ffile.write(",".join("true" if f else "false" for fl in flags for f in fl) + "\n")
                 stats_out["iterations"] = it
+                stats_out["loop_s"] = ll
     finally:
         ctx.close()
         if ffile is not None:
