@@ -82,9 +82,14 @@ __device__ __forceinline__ void build_row_feature(const DsDev& ds, const PoolDev
     double sum = 0.0, beta = 0.5, mu = 0.0, lam = 1.0;
     if (on) {
       const double* x = (const double*)ds.x;
+      // the member's value is fetched two members ahead of the dependent arithmetic
+      double x1 = cnt > 0 ? x[(size_t)mem[0] * ds.Dp + q] : 0.0;
+      double x2 = cnt > 1 ? x[(size_t)mem[1] * ds.Dp + q] : 0.0;
       for (int t = 0; t < cnt; ++t) {
         const double nn = (double)(t + 1);
-        const double xv = x[(size_t)mem[t] * ds.Dp + q];
+        const double xv = x1;
+        x1 = x2;
+        if (t + 2 < cnt) x2 = x[(size_t)mem[t + 2] * ds.Dp + q];
         sum = __dadd_rn(sum, xv);
         const double dd = __dadd_rn(xv, -mu);
         beta = __dadd_rn(beta, __ddiv_rn(__dmul_rn(__dadd_rn(__dadd_rn(nn, -1.0), 0.001), __dmul_rn(dd, dd)),
