@@ -107,6 +107,7 @@ struct __attribute__((aligned(16))) SweepParams {
   int4* elist;            /* spec engine: [2][E-CTAs][lcap] the E-CTAs' copies of the list beyond shared memory */
   long long lcap;
   int fc_target;          /* spec engine: free-row ids an E-CTA keeps cached per dataset        */
+  int plan_smem;          /* spec engine: the resampling plan's scratch fits the D-CTA's shared memory */
   int pad1;
   unsigned long long* rows_add;  /* [K] clusters that had an observation added (pool / spec engines) */
   /* pool / spec engines: the barrier counters and the step tags of the rank partials run on from sweep to

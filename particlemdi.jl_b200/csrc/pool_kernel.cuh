@@ -535,18 +535,20 @@ __device__ __noinline__ void pool_propose(const SweepParams& sp, PoolSmem& sm, c
 // anc[0] == 1).  The Fisher-Yates shuffle followed by partstar[1]=1 and sort! only decides WHICH
 // element of the sorted systematic sample the reference particle replaces: the one the shuffle
 // moves to position 1; that index is traced through the swaps without moving anything.
+// Scratch of the plan (P entries each): global memory, or the calling CTA's shared memory when it has room.
+struct PlanScratch { double *w, *pp, *u; int *j, *a0; };
 __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step, int ev, double mx, int* s_tmp,
-                                                const double* lw = nullptr) {
+                                                const double* lw, const PlanScratch sc) {
   if (!lw) lw = sp.lw;  // (the spec engine keeps two copies of the log-weights, by step parity)
   const int P = sp.P, t = threadIdx.x;
 #pragma unroll 1
   for (int p = t; p < P; p += PMDI_NT) {
-    sp.sc_w[p] = pm_exp(__ldcg(on_rank(sp, lw + p, p / sp.Ps)) - mx);  // the holder's copy (NVLink when remote)
+    sc.w[p] = pm_exp(__ldcg(on_rank(sp, lw + p, p / sp.Ps)) - mx);  // the holder's copy (NVLink when remote)
     const double us = sp.tape_shuffle ? sp.tape_shuffle[(size_t)step * P + p]
                                       : pm_uniform(sp.seed, sp.iter, DRAW_SHUFFLE, step, 0, p);
     int jj = 1 + (int)floor(us * (double)(p + 1));
     if (jj > p + 1) jj = p + 1;
-    sp.sc_j[p] = jj;
+    sc.j[p] = jj;
   }
   __syncthreads();
   if (t == 0) {  // pprob = cumsum(exp.(logweight .- max)), sequential (misc.jl:29); loads sixteen ahead of the adds
@@ -556,52 +558,52 @@ __device__ __noinline__ void pool_resample_plan(const SweepParams& sp, int step,
     for (; p + 16 <= P; p += 16) {
       double v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __ldcg(sp.sc_w + p + i);
+      for (int i = 0; i < 16; ++i) v[i] = sc.w[p + i];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) { acc += v[i]; sp.sc_pp[p + i] = acc; }
+      for (int i = 0; i < 16; ++i) { acc += v[i]; sc.pp[p + i] = acc; }
     }
 #pragma unroll 1
-    for (; p < P; ++p) { acc += sp.sc_w[p]; sp.sc_pp[p] = acc; }
+    for (; p < P; ++p) { acc += sc.w[p]; sc.pp[p] = acc; }
   } else if (t == 32) {  // u, u + 1/P, ... by repeated addition (misc.jl:28,35)
     const double r = sp.tape_resamp ? sp.tape_resamp[step] : pm_uniform(sp.seed, sp.iter, DRAW_RESAMP, step, 0, 0);
     double u = r / (double)P;
 #pragma unroll 1
-    for (int i = 0; i < P; ++i) { sp.sc_u[i] = u; u += 1.0 / (double)P; }
+    for (int i = 0; i < P; ++i) { sc.u[i] = u; u += 1.0 / (double)P; }
   } else if (t == 64) {  // index of the pre-shuffle element that ends at position 1
     int tt = 0, pos = 2;
 #pragma unroll 1
     for (; pos + 15 <= P; pos += 16) {
       int v[16];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = __ldcg(sp.sc_j + pos - 1 + i);
+      for (int i = 0; i < 16; ++i) v[i] = sc.j[pos - 1 + i];
 #pragma unroll
       for (int i = 0; i < 16; ++i)
         if (v[i] - 1 == tt) tt = pos - 1 + i;
     }
 #pragma unroll 1
     for (; pos <= P; ++pos)
-      if (sp.sc_j[pos - 1] - 1 == tt) tt = pos - 1;
+      if (sc.j[pos - 1] - 1 == tt) tt = pos - 1;
     s_tmp[0] = tt;
   }
   __syncthreads();
-  const double tot = sp.sc_pp[P - 1];
+  const double tot = sc.pp[P - 1];
 #pragma unroll 1
   for (int i = t; i < P; i += PMDI_NT) {  // first p with pprob[p]/last >= u_i (misc.jl:33-38)
-    const double ui = sp.sc_u[i];
+    const double ui = sc.u[i];
     int lo = 0, hi = P;
 #pragma unroll 1
     while (lo < hi) {
       const int mid = (lo + hi) >> 1;
-      if (pm_div(sp.sc_pp[mid], tot) >= ui) hi = mid; else lo = mid + 1;
+      if (pm_div(sc.pp[mid], tot) >= ui) hi = mid; else lo = mid + 1;
     }
-    sp.sc_anc0[i] = (lo < P) ? lo + 1 : P;
+    sc.a0[i] = (lo < P) ? lo + 1 : P;
   }
   __syncthreads();
   const int drop = s_tmp[0];
   int* anc = sp.anc_log + (size_t)ev * P;
 #pragma unroll 1
   for (int i = t; i < P; i += PMDI_NT) {
-    const int a = (i == 0) ? 1 : ((i - 1 < drop) ? sp.sc_anc0[i - 1] : sp.sc_anc0[i]);
+    const int a = (i == 0) ? 1 : ((i - 1 < drop) ? sc.a0[i - 1] : sc.a0[i]);
     anc[i] = a;
     if (sp.dbg_anc) sp.dbg_anc[(size_t)step * P + i] = a;
   }
@@ -679,7 +681,8 @@ __device__ __noinline__ bool pool_resample(const SweepParams& sp, PoolSmem& sm, 
   const long long gt = (long long)blockIdx.x * PMDI_NT + threadIdx.x, GT = (long long)sp.G * PMDI_NT;
   // every CTA of every rank: deferred bookkeeping in, this step's log-weights and evaluations final
   if (!pool_xsync(sp, sm)) return false;
-  if (blockIdx.x == 0) pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp);
+  if (blockIdx.x == 0)
+    pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp, nullptr, PlanScratch{sp.sc_w, sp.sc_pp, sp.sc_u, sp.sc_j, sp.sc_anc0});
   if (!pool_gsync(sp, sm)) return false;
   const int* anc = sp.anc_log + (size_t)ev * sp.P;
   if (gt == 0 && st + 1 < sp.steps) {  // rows the E phase evaluated ahead of this decision (live now, dead after it)

@@ -491,22 +491,26 @@ __device__ __forceinline__ int spec_pop_id(const SweepParams& sp, SpecSmem& sm, 
 // keep the caches around their target height (thread k < K), off the step's dependent chain: the CTA that
 // owns an entry frees its ids, the CTA that runs a task takes ids - the two drift apart
 __device__ __forceinline__ void spec_refill(const SweepParams& sp, SpecSmem& sm, const SpecTables& T) {
-  const int k = threadIdx.x;
+  const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;  // warp k: dataset k, a lane per id (one atomic round trip each)
   if (k >= sp.K) return;
   const PoolDev& pd = sp.pd[k];
   const int top = T.fc_top[k], tgt = sp.fc_target;
+  __syncwarp();
   if (top < tgt / 2) {
     const int want = tgt - top;
-    const int first = spec_gclaim(pd, want);
+    int first = lane == 0 ? spec_gclaim(pd, want) : 0;
+    first = __shfl_sync(FULL, first, 0);
     if (first < 0) return;  // nearly dry: spec_pop_id reports a real exhaustion
 #pragma unroll 1
-    for (int i = 0; i < want; ++i) T.fc_s[k * SPEC_FC + top + i] = spec_gtake(pd, first + i);
-    T.fc_top[k] = top + want;
+    for (int i = lane; i < want; i += 32) T.fc_s[k * SPEC_FC + top + i] = spec_gtake(pd, first + i);
+    __syncwarp();
+    if (lane == 0) T.fc_top[k] = top + want;
   } else if (top > SPEC_FC - 32 || top > 2 * tgt + 16) {
     const int keep = min(SPEC_FC / 2, tgt + 8);
 #pragma unroll 1
-    for (int i = keep; i < top; ++i) spec_gpush(pd, T.fc_s[k * SPEC_FC + i]);
-    T.fc_top[k] = keep;
+    for (int i = keep + lane; i < top; i += 32) spec_gpush(pd, T.fc_s[k * SPEC_FC + i]);
+    __syncwarp();
+    if (lane == 0) T.fc_top[k] = keep;
   }
 }
 
@@ -592,23 +596,33 @@ __device__ __noinline__ void spec_fix(const SweepParams& sp, SpecSmem& sm, const
       const int up = __shfl_up_sync(FULL, incl, o);
       if (lane >= o) incl += up;
     }
-    if (lane == 31) sm.wsum[warp] = incl;
-    __syncthreads();
-    int wpre = 0, tot_all = 0;
+    if (n_old <= 32) {  // the whole list is in the first warp (the usual case of a settled chain): no CTA barrier
+      if (warp == 0) {
+        const int pos = incl - ns;
+        if (ns > 0) spec_set_entry(sp, T, e, ln, pos, s0);
+        if (ns > 1) spec_set_entry(sp, T, e, ln, pos + 1, s1);
+        nb = __shfl_sync(FULL, incl, 31);
+      }
+    } else {
+      if (lane == 31) sm.wsum[warp] = incl;
+      __syncthreads();
+      int wpre = 0, tot_all = 0;
 #pragma unroll
-    for (int w = 0; w < POOL_NW; ++w) {
-      const int x = sm.wsum[w];
-      if (w < warp) wpre += x;
-      tot_all += x;
+      for (int w = 0; w < POOL_NW; ++w) {
+        const int x = sm.wsum[w];
+        if (w < warp) wpre += x;
+        tot_all += x;
+      }
+      const int pos = nb + wpre + incl - ns;
+      if (ns > 0) spec_set_entry(sp, T, e, ln, pos, s0);
+      if (ns > 1) spec_set_entry(sp, T, e, ln, pos + 1, s1);
+      nb += tot_all;
+      __syncthreads();
     }
-    const int pos = nb + wpre + incl - ns;
-    if (ns > 0) spec_set_entry(sp, T, e, ln, pos, s0);
-    if (ns > 1) spec_set_entry(sp, T, e, ln, pos + 1, s1);
-    nb += tot_all;
-    __syncthreads();
     STRACE(t1 + 1, 62)
   }
   if (n_old == 0) __syncthreads();  // b_* are complete
+  else if (n_old <= 32) __syncwarp();  // ... written and read by the first warp
   // births, in dataset order; their side effects by the E-CTAs in turn
 #pragma unroll 1
   for (int k = 0; k < K; ++k) {
@@ -635,7 +649,7 @@ __device__ __noinline__ void spec_fix(const SweepParams& sp, SpecSmem& sm, const
 // time, a row's blocks over jq warps, the block partials meet in shared memory.
 template <bool DBG>
 __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, const SpecTables& T, int e, int st,
-                                       unsigned char* xring, int& obs_ok) {
+                                       unsigned char* xring, int& obs_ok, int t_dec) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int K = sp.K, par = st & 1, GE = sp.G - sp.GP - 1;
   const int jq = sp.jq, rpc = POOL_NW / jq;
@@ -728,6 +742,20 @@ __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, cons
     }
     STRACE(st - 1, 66)
   }
+  // the decision on the resampling after step t_dec (published by the D-CTA early in this phase) is
+  // fetched by a thread that has nothing to finish; the barrier below hands it to the CTA
+  if (t_dec >= 0 && threadIdx.x == 32) {
+    int d;
+    const unsigned long long t0 = globaltimer_ns();
+    unsigned spins = 0;
+#pragma unroll 1
+    while ((d = *(volatile unsigned char*)(sp.dec + t_dec)) == 0) {
+      if (((++spins) & 0x3ffu) == 0 && (__ldcg(sp.err) != 0 || globaltimer_ns() - t0 > sp.wd_ns)) {
+        atomicCAS(sp.err, 0, 77); sm.fail = 1; break;
+      }
+    }
+    sm.res_flag = d == 2;
+  }
   __syncthreads();
 }
 
@@ -804,8 +832,15 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
 #define RS_MARK(i_) if (tm) { const unsigned long long n_ = globaltimer_ns(); sm.tacc[i_] += (n_ - t_) * POOL_NW; t_ = n_; }
   // every E-CTA (of every rank) has finished E'(st+2), every commit of step st is in
   if (!spec_xsync(sp, sm)) return false;
-  if ((int)blockIdx.x == sp.G - 1)  // the D-CTA knows the maximum
-    pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp, sp.lw + (size_t)(st & 1) * sp.P);
+  if ((int)blockIdx.x == sp.G - 1) {  // the D-CTA knows the maximum; its dynamic shared memory is free for the plan
+    extern __shared__ __align__(16) unsigned char plan_raw[];  // (the dynamic shared memory, from its base)
+    PlanScratch sc = {sp.sc_w, sp.sc_pp, sp.sc_u, sp.sc_j, sp.sc_anc0};
+    if (sp.plan_smem) {
+      sc.w = (double*)plan_raw; sc.pp = sc.w + sp.P; sc.u = sc.pp + sp.P;
+      sc.j = (int*)(sc.u + sp.P); sc.a0 = sc.j + sp.P;
+    }
+    pool_resample_plan(sp, st, ev, sm.res_mx, s_tmp, sp.lw + (size_t)(st & 1) * sp.P, sc);
+  }
   if (!spec_gsync(sp, sm)) return false;
   RS_MARK(4)
   const int* anc = sp.anc_log + (size_t)ev * sp.P;
@@ -1069,7 +1104,7 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
   int obs_ok = -1;
   const bool is_d = cta == sp.G - 1;  // the CTA that decides on the resamplings
   // ---- A(-1): the predictive of x[0] for every live row, and the ids of the first children
-  if (!is_p && !is_d) spec_eval<DBG>(sp, sm, T, e, 0, xring, obs_ok);
+  if (!is_p && !is_d) spec_eval<DBG>(sp, sm, T, e, 0, xring, obs_ok, -1);
   PHASE_MARK(1)
   if (!spec_gsync(sp, sm)) return;
   PHASE_MARK(0)
@@ -1122,13 +1157,15 @@ __device__ __forceinline__ void spec_sweep_body(const SweepParams& sp, SpecSmem&
       if (e == 0 && tid < K) { sm.rows_eval[tid] += (unsigned)sm.kc[tid] + 1u; sm.kc[tid] = 0; }  // the next fix counts afresh
       PHASE_MARK(3)
       STRACE(t, 51)
-      if (t + 1 < steps) spec_eval<DBG>(sp, sm, T, e, t + 1, xring, obs_ok);
+      if (t + 1 < steps) spec_eval<DBG>(sp, sm, T, e, t + 1, xring, obs_ok, t - 1);
       PHASE_MARK(1)
       STRACE(t, 52)
       spec_refill(sp, sm, T);
-      if (t > 0) {  // the decision on the resampling after step t-1 (published long ago)
-        __syncthreads();
-        if (!spec_wait_decision(sp, sm, t - 1)) return;
+      if (t > 0) {  // the decision on the resampling after step t-1: fetched inside the evaluation
+        if (t + 1 >= steps) {
+          __syncthreads();
+          if (!spec_wait_decision(sp, sm, t - 1)) return;
+        } else if (sm.fail) return;
         if (sm.res_flag) {
           if (!spec_resample(sp, sm, T, ns, t - 1, s_tmp, false, e)) return;
           PHASE_MARK(6)

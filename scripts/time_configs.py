@@ -27,11 +27,12 @@ with capi.Context(cfg["data"], cfg["types"], cfg["N"], cfg["P"]) as ctx:
     s = hy["s"]
     for it in range(sweeps):
         r = ctx.sweep(s, rng.permutation(cfg["n"]) + 1, n1, hy["Pi"], hy["phi"], seed=9, it=it,
-                      logweight_init=float(it > 0), time_phases=(it == sweeps - 1))
+                      logweight_init=float(it > 0), time_phases=(it == sweeps - 1) or bool(os.environ.get('PMDI_TIME_ALL')))
         s = r["s"]
         rows.append(dict(sweep=it, kernel_ms=round(r["sweep_kernel_ms"], 3), device_ms=round(r["device_ms"], 3),
                          rows_evaluated=sum(r["rows_evaluated"]), rows_referenced=sum(r["rows_referenced"]),
-                         resamples=r["n_resamples"], engine=r["engine"]))
+                         resamples=r["n_resamples"], engine=r["engine"],
+                         **({'phase_ms': [round(v, 3) for v in r['phase_ms']]} if os.environ.get('PMDI_TIME_ALL') else {})))
         print(json.dumps(rows[-1]), flush=True)
     steps = cfg["n"] - n1 + 1
     print(json.dumps(dict(config=name, over=over, steps=steps, us_per_step=round(1e3 * rows[-1]["kernel_ms"] / steps, 2),
