@@ -120,6 +120,8 @@ struct __attribute__((aligned(16))) SweepParams {
   int4* pull_jobs;        /* resampling: (dataset, source rank, source row, local row) of rows to pull */
   int* pull_map;          /* spec engine, several ranks: [K][R][cap] local copy of a remote row during a resampling (-1: none) */
   double* rank_part;      /* [2][R][4] per step parity and rank: max, sum w, sum w^2, step tag */
+  unsigned long long* rank_words; /* spec engine: [2][R][8] the same three doubles as six (tag << 32 | half) words: no fence */
+  unsigned tag32;         /* ... tag of step t = tag32 + t + 1 (runs on over the sweeps of a context)          */
   unsigned long long* rows_ref; /* [K] occupied (particle, label) rows referenced by proposals */
   const double* Pi;      /* [K][N]                                          */
   const double* l1phi;   /* [npairs] log(1+phi)                             */

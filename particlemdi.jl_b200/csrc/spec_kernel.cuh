@@ -354,41 +354,42 @@ __device__ __noinline__ void spec_decide(const SweepParams& sp, SpecSmem& sm, in
     a = warp_sum(a);
     b = warp_sum(b);
     double gmx = mx;
-    if (sp.R > 1) {  // one (max, sum w, sum w^2) per rank, pushed to every rank with the step as its tag
+    if (sp.R > 1) {
+      // One (max, sum w, sum w^2) per rank goes to every rank as six 8-byte words (step tag << 32 | half of a
+      // double): each word validates itself, so the stores need no fence and no ordering - one NVLink one-way
+      // trip instead of a round trip (the fence) plus a trip (the tag).  Slots by step parity: a peer cannot
+      // be two steps ahead, it needs this rank's partial of step t+1 first.
       const int par = t & 1;
-      double* mine = sp.rank_part + ((size_t)par * sp.R + sp.rank) * 4;
-      if (lane == 0) {
+      const unsigned tag = sp.tag32 + (unsigned)(t + 1);
+      unsigned long long* words = sp.rank_words + (size_t)par * sp.R * 8;
+      if (lane < 6) {
+        const double val = (lane >> 1) == 0 ? mx : (lane >> 1) == 1 ? a : b;
+        const unsigned half = (lane & 1) ? (unsigned)__double2hiint(val) : (unsigned)__double2loint(val);
+        const unsigned long long word = ((unsigned long long)tag << 32) | half;
 #pragma unroll 1
-        for (int r = 0; r < sp.R; ++r) {
-          double* q = on_rank(sp, mine, r);
-          __stcg(q, mx); __stcg(q + 1, a); __stcg(q + 2, b);
-        }
-        // ONE system fence orders all the partials before all the tags (a release store per rank would pay a
-        // round trip over NVLink each: 8 ranks -> ~20 us, longer than the step the decision has to arrive in)
-        __threadfence_system();
-#pragma unroll 1
-        for (int r = 0; r < sp.R; ++r) {
-          unsigned long long* f = (unsigned long long*)(on_rank(sp, mine, r) + 3);
-          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(f), "l"(sp.tag_base + (unsigned long long)(t + 1)) : "memory");
-        }
+        for (int r = 0; r < sp.R; ++r)
+          asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(on_rank(sp, words + (size_t)sp.rank * 8 + lane, r)), "l"(word) : "memory");
       }
-      const double* base = sp.rank_part + (size_t)par * sp.R * 4;
-      if (lane < sp.R) {
-        const unsigned long long* f = (const unsigned long long*)(base + (size_t)lane * 4 + 3);
+      unsigned* hw = (unsigned*)&sm.red[1][0][0];  // the halves as they arrive: [rank][6]
+#pragma unroll 1
+      for (int idx = lane; idx < 6 * sp.R; idx += 32) {
+        const unsigned long long* f = words + (size_t)(idx / 6) * 8 + (idx % 6);
         const unsigned long long t0 = globaltimer_ns();
         unsigned spins = 0;
-        while (ld_acquire_sys_u64(f) < sp.tag_base + (unsigned long long)(t + 1)) {
+        unsigned long long w;
+        while ((unsigned)((w = *(volatile const unsigned long long*)f) >> 32) != tag) {
           if (((++spins) & 0x3ffu) == 0 && (__ldcg(sp.err) != 0 || globaltimer_ns() - t0 > sp.wd_ns)) { atomicExch(sp.err, 77); break; }
         }
+        hw[idx] = (unsigned)w;
       }
       __syncwarp();
-      const double rm = lane < sp.R ? ldcg_f64(base + (size_t)lane * 4) : -INFINITY;
+      const double rm = lane < sp.R ? __hiloint2double((int)hw[lane * 6 + 1], (int)hw[lane * 6]) : -INFINITY;
       gmx = warp_max(rm);
       double ra = 0.0, rb = 0.0;
       if (lane < sp.R && rm > -INFINITY) {
         const double e = pm_exp(rm - gmx);
-        ra = ldcg_f64(base + (size_t)lane * 4 + 1) * e;
-        rb = ldcg_f64(base + (size_t)lane * 4 + 2) * (e * e);
+        ra = __hiloint2double((int)hw[lane * 6 + 3], (int)hw[lane * 6 + 2]) * e;
+        rb = __hiloint2double((int)hw[lane * 6 + 5], (int)hw[lane * 6 + 4]) * (e * e);
       }
       a = warp_sum(ra);
       b = warp_sum(rb);
@@ -759,48 +760,64 @@ __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, cons
   __syncthreads();
 }
 
-// One warp copies a live row of another rank's pool and that row's child of the coming step into local rows
-// (statistics, aux, cluster sizes, the predictives already computed for the next two observations) and
-// points their child links at the local ids handed to it.
-__device__ __noinline__ void spec_row_pull(const SweepParams& sp, int4 j0, int4 j1, int parn) {
+// A live row of another rank's pool and that row's child of the coming step are copied into local rows
+// (statistics, aux, cluster sizes, the predictives already computed for the next two observations) with
+// their child links pointed at the local ids handed to them.  A job is cut into SPEC_PULL_PARTS pieces
+// (row / child x 8 slices of the statistics), a warp per piece, eight 16-byte loads in flight per lane:
+// an NVLink round trip is ~2 us, a piece costs two or three of them.
+#define SPEC_PULL_PARTS 16
+__device__ __forceinline__ void spec_copy16(void* dst, const void* src, long long n16, int lane) {
+  const int4* s = (const int4*)src;
+  int4* d = (int4*)dst;
+#pragma unroll 1
+  for (long long b = 0; b < n16; b += 256) {
+    int4 v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long q = b + lane + 32 * i;
+      if (q < n16) v[i] = __ldcg(s + q);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const long long q = b + lane + 32 * i;
+      if (q < n16) d[q] = v[i];
+    }
+  }
+}
+__device__ __noinline__ void spec_row_pull(const SweepParams& sp, int4 j0, int4 j1, int parn, int part) {
   const int k = j0.x & 0xff, ra = j0.x >> 8, rb = j0.y, v2 = j0.z, c2 = j0.w, a2 = j1.x, b2 = j1.y;
   const DsDev& ds = sp.ds[k];
   const PoolDev& pd = sp.pd[k];
   const long long sdelta = sp.peer_delta[ra];
   const int lane = threadIdx.x & 31, Dp = ds.Dp;
+  const int h = part & 1, ch = part >> 1;  // row or child; slice 0..7
 #define PMDI_SRC(ptr_) ((decltype(ptr_))((const char*)(ptr_) + sdelta))
   const RowInfo* rinfo = PMDI_SRC(pd.info);
-  const int4 i1 = ldcg_info(rinfo + (size_t)parn * pd.cap + rb);           // step st+1: lp, child
+  int4 i1 = make_int4(0, 0, 0, 0);
+  if (h || part == 0) i1 = ldcg_info(rinfo + (size_t)parn * pd.cap + rb);  // step st+1: lp, child
   const int rc = i1.z;
-  const int4 i2 = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rb);     // step st+2: lp of the row
-  const int4 i2c = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rc);    //            lp of its child
-  const int n = ldcg_i32(PMDI_SRC(ds.n) + rb);
-#pragma unroll 1
-  for (int h = 0; h < 2; ++h) {
-    const long long src = h ? rc : rb, dst = h ? c2 : v2;
-    if (ds.type == T_GAUSSIAN) {
-#pragma unroll 1
-      for (int q = 2 * lane; q < Dp; q += 64) {
-        const double2 a = ldcg_f64x2(PMDI_SRC(ds.mu) + src * Dp + q), b = ldcg_f64x2(PMDI_SRC(ds.lamn) + src * Dp + q);
-        const double2 c = ldcg_f64x2(PMDI_SRC(ds.sum) + src * Dp + q), d = ldcg_f64x2(PMDI_SRC(ds.beta) + src * Dp + q);
-        *(double2*)(ds.mu + dst * Dp + q) = a; *(double2*)(ds.lamn + dst * Dp + q) = b;
-        *(double2*)(ds.sum + dst * Dp + q) = c; *(double2*)(ds.beta + dst * Dp + q) = d;
-      }
-    } else if (ds.type == T_CATEGORICAL) {
-      const long long W = (long long)Dp * pd.wpf;
-#pragma unroll 1
-      for (long long q = 2 * lane; q < W; q += 64)
-        *(ulonglong2*)(pd.cw + dst * W + q) = ldcg_u64x2(PMDI_SRC(pd.cw) + src * W + q);
-    } else {
-#pragma unroll 1
-      for (int q = 2 * lane; q < Dp; q += 64)
-        *(longlong2*)(ds.S + dst * Dp + q) = ldcg_i64x2(PMDI_SRC(ds.S) + src * Dp + q);
+  const long long src = h ? rc : rb, dst = h ? c2 : v2;
+  if (ds.type == T_GAUSSIAN) {  // four arrays, two halves each
+    const int arr = ch >> 1, sg = ch & 1;
+    double* base = arr == 0 ? ds.mu : arr == 1 ? ds.lamn : arr == 2 ? ds.sum : ds.beta;
+    const long long n16 = Dp / 2, per = (n16 + 1) / 2, o = sg * per;
+    spec_copy16(base + dst * Dp + 2 * o, PMDI_SRC(base) + src * Dp + 2 * o, min(per, n16 - o), lane);
+  } else {
+    const long long W = ds.type == T_CATEGORICAL ? (long long)Dp * pd.wpf : (long long)Dp;  // 8-byte words of a row
+    const long long n16 = W / 2, per = (n16 + 7) / 8, o = ch * per;
+    if (o < n16) {
+      if (ds.type == T_CATEGORICAL) spec_copy16(pd.cw + dst * W + 2 * o, PMDI_SRC(pd.cw) + src * W + 2 * o, min(per, n16 - o), lane);
+      else spec_copy16(ds.S + dst * W + 2 * o, PMDI_SRC(ds.S) + src * W + 2 * o, min(per, n16 - o), lane);
     }
+  }
+  if (ch == 0) {
 #pragma unroll 1
     for (int jj = lane; jj < ds.J; jj += 32) ds.aux[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + jj);
   }
-#undef PMDI_SRC
-  if (lane == 0) {
+  if (part == 0 && lane == 0) {
+    const int4 i2 = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rb);     // step st+2: lp of the row
+    const int4 i2c = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rc);    //            lp of its child
+    const int n = ldcg_i32(PMDI_SRC(ds.n) + rb);
     ds.n[v2] = n; ds.n[c2] = n + 1; ds.n[a2] = n + 1; ds.n[b2] = n + 2;
     int4 w = i1; w.z = c2; w.w = 0;
     *(int4*)(pd.info + (size_t)parn * pd.cap + v2) = w;
@@ -809,6 +826,7 @@ __device__ __noinline__ void spec_row_pull(const SweepParams& sp, int4 j0, int4 
     w = i2c; w.z = b2; w.w = 0;
     *(int4*)(pd.info + (size_t)(parn ^ 1) * pd.cap + c2) = w;
   }
+#undef PMDI_SRC
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -906,10 +924,12 @@ __device__ __noinline__ bool spec_resample(const SweepParams& sp, SpecSmem& sm, 
     const long long njobs = __ldcg(&sp.counters[5]);
     const long long gw = gt >> 5, GWp = GT >> 5;
 #pragma unroll 1
-    for (long long job = gw; job < njobs; job += GWp) {
+    for (long long item = gw; item < njobs * SPEC_PULL_PARTS; item += GWp) {
+      const long long job = item / SPEC_PULL_PARTS;
+      const int part = (int)(item - job * SPEC_PULL_PARTS);
       const int4 j0 = __ldcg(sp.pull_jobs + 2 * job);
-      spec_row_pull(sp, j0, __ldcg(sp.pull_jobs + 2 * job + 1), parn);
-      if ((threadIdx.x & 31) == 0)  // the map is clear again for the next resampling
+      spec_row_pull(sp, j0, __ldcg(sp.pull_jobs + 2 * job + 1), parn, part);
+      if (part == 0 && (threadIdx.x & 31) == 0)  // the map is clear again for the next resampling
         __stcg(sp.pull_map + ((size_t)(j0.x & 0xff) * sp.R + (j0.x >> 8)) * sp.pd[j0.x & 0xff].cap + j0.y, -1);
     }
     if (gt == 0) sp.counters[3] += njobs;
