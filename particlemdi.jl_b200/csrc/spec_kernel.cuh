@@ -760,64 +760,54 @@ __device__ __noinline__ void spec_eval(const SweepParams& sp, SpecSmem& sm, cons
   __syncthreads();
 }
 
-// A live row of another rank's pool and that row's child of the coming step are copied into local rows
-// (statistics, aux, cluster sizes, the predictives already computed for the next two observations) with
-// their child links pointed at the local ids handed to them.  A job is cut into SPEC_PULL_PARTS pieces
-// (row / child x 8 slices of the statistics), a warp per piece, eight 16-byte loads in flight per lane:
-// an NVLink round trip is ~2 us, a piece costs two or three of them.
+// One warp copies a slice (1 / SPEC_PULL_PARTS of the features) of a live row of another rank's pool and of that
+// row's child of the coming step into local rows; the warp of slice 0 also copies aux, the cluster sizes and the
+// predictives already computed for the next two observations, and points the child links at the local ids
+// handed to the copy.  (An NVLink round trip is ~2 us: a whole row per warp was 30-60 of them in a row.)
 #define SPEC_PULL_PARTS 16
-__device__ __forceinline__ void spec_copy16(void* dst, const void* src, long long n16, int lane) {
-  const int4* s = (const int4*)src;
-  int4* d = (int4*)dst;
-#pragma unroll 1
-  for (long long b = 0; b < n16; b += 256) {
-    int4 v[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const long long q = b + lane + 32 * i;
-      if (q < n16) v[i] = __ldcg(s + q);
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const long long q = b + lane + 32 * i;
-      if (q < n16) d[q] = v[i];
-    }
-  }
-}
 __device__ __noinline__ void spec_row_pull(const SweepParams& sp, int4 j0, int4 j1, int parn, int part) {
   const int k = j0.x & 0xff, ra = j0.x >> 8, rb = j0.y, v2 = j0.z, c2 = j0.w, a2 = j1.x, b2 = j1.y;
   const DsDev& ds = sp.ds[k];
   const PoolDev& pd = sp.pd[k];
   const long long sdelta = sp.peer_delta[ra];
   const int lane = threadIdx.x & 31, Dp = ds.Dp;
-  const int h = part & 1, ch = part >> 1;  // row or child; slice 0..7
 #define PMDI_SRC(ptr_) ((decltype(ptr_))((const char*)(ptr_) + sdelta))
   const RowInfo* rinfo = PMDI_SRC(pd.info);
-  int4 i1 = make_int4(0, 0, 0, 0);
-  if (h || part == 0) i1 = ldcg_info(rinfo + (size_t)parn * pd.cap + rb);  // step st+1: lp, child
+  const int4 i1 = ldcg_info(rinfo + (size_t)parn * pd.cap + rb);           // step st+1: lp, child
   const int rc = i1.z;
-  const long long src = h ? rc : rb, dst = h ? c2 : v2;
-  if (ds.type == T_GAUSSIAN) {  // four arrays, two halves each
-    const int arr = ch >> 1, sg = ch & 1;
-    double* base = arr == 0 ? ds.mu : arr == 1 ? ds.lamn : arr == 2 ? ds.sum : ds.beta;
-    const long long n16 = Dp / 2, per = (n16 + 1) / 2, o = sg * per;
-    spec_copy16(base + dst * Dp + 2 * o, PMDI_SRC(base) + src * Dp + 2 * o, min(per, n16 - o), lane);
-  } else {
-    const long long W = ds.type == T_CATEGORICAL ? (long long)Dp * pd.wpf : (long long)Dp;  // 8-byte words of a row
-    const long long n16 = W / 2, per = (n16 + 7) / 8, o = ch * per;
-    if (o < n16) {
-      if (ds.type == T_CATEGORICAL) spec_copy16(pd.cw + dst * W + 2 * o, PMDI_SRC(pd.cw) + src * W + 2 * o, min(per, n16 - o), lane);
-      else spec_copy16(ds.S + dst * W + 2 * o, PMDI_SRC(ds.S) + src * W + 2 * o, min(per, n16 - o), lane);
+  const int4 i2 = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rb);     // step st+2: lp of the row
+  const int4 i2c = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rc);    //            lp of its child
+  const int n = ldcg_i32(PMDI_SRC(ds.n) + rb);
+  const long long W = ds.type == T_CATEGORICAL ? (long long)Dp * pd.wpf : (long long)Dp;  // 8-byte words per array of a row
+  const long long per = ((W / 64 + SPEC_PULL_PARTS - 1) / SPEC_PULL_PARTS) * 64;
+  const long long q_lo = part * per, q_hi = min(W, q_lo + per);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    const long long src = h ? rc : rb, dst = h ? c2 : v2;
+    if (ds.type == T_GAUSSIAN) {
+#pragma unroll 1
+      for (long long q = q_lo + 2 * lane; q < q_hi; q += 64) {
+        const double2 a = ldcg_f64x2(PMDI_SRC(ds.mu) + src * Dp + q), b = ldcg_f64x2(PMDI_SRC(ds.lamn) + src * Dp + q);
+        const double2 c = ldcg_f64x2(PMDI_SRC(ds.sum) + src * Dp + q), d = ldcg_f64x2(PMDI_SRC(ds.beta) + src * Dp + q);
+        *(double2*)(ds.mu + dst * Dp + q) = a; *(double2*)(ds.lamn + dst * Dp + q) = b;
+        *(double2*)(ds.sum + dst * Dp + q) = c; *(double2*)(ds.beta + dst * Dp + q) = d;
+      }
+    } else if (ds.type == T_CATEGORICAL) {
+#pragma unroll 1
+      for (long long q = q_lo + 2 * lane; q < q_hi; q += 64)
+        *(ulonglong2*)(pd.cw + dst * W + q) = ldcg_u64x2(PMDI_SRC(pd.cw) + src * W + q);
+    } else {
+#pragma unroll 1
+      for (long long q = q_lo + 2 * lane; q < q_hi; q += 64)
+        *(longlong2*)(ds.S + dst * Dp + q) = ldcg_i64x2(PMDI_SRC(ds.S) + src * Dp + q);
+    }
+    if (part == 0) {
+#pragma unroll 1
+      for (int jj = lane; jj < ds.J; jj += 32) ds.aux[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + jj);
     }
   }
-  if (ch == 0) {
-#pragma unroll 1
-    for (int jj = lane; jj < ds.J; jj += 32) ds.aux[dst * ds.J + jj] = ldcg_f64(PMDI_SRC(ds.aux) + src * ds.J + jj);
-  }
-  if (part == 0 && lane == 0) {
-    const int4 i2 = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rb);     // step st+2: lp of the row
-    const int4 i2c = ldcg_info(rinfo + (size_t)(parn ^ 1) * pd.cap + rc);    //            lp of its child
-    const int n = ldcg_i32(PMDI_SRC(ds.n) + rb);
+#undef PMDI_SRC
+  if (lane == 0 && part == 0) {
     ds.n[v2] = n; ds.n[c2] = n + 1; ds.n[a2] = n + 1; ds.n[b2] = n + 2;
     int4 w = i1; w.z = c2; w.w = 0;
     *(int4*)(pd.info + (size_t)parn * pd.cap + v2) = w;
@@ -826,7 +816,6 @@ __device__ __noinline__ void spec_row_pull(const SweepParams& sp, int4 j0, int4 
     w = i2c; w.z = b2; w.w = 0;
     *(int4*)(pd.info + (size_t)(parn ^ 1) * pd.cap + c2) = w;
   }
-#undef PMDI_SRC
 }
 
 // ------------------------------------------------------------------------------------------------

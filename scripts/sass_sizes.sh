@@ -2,7 +2,7 @@
 # sizes (bytes of SASS) of the sub-functions of a kernel in libpmdi_cuda.so: scripts/sass_sizes.sh k_sweep_pool
 K=${1:-k_sweep_pool}
 D=$(mktemp -d); cd $D
-cuobjdump -xelf all /root/repo/particlemdi.jl_b200/libpmdi_cuda.so >/dev/null 2>&1
+cuobjdump -xelf all ${PMDI_LIB:-/root/repo/particlemdi.jl_b200/libpmdi_cuda.so} >/dev/null 2>&1
 nvdisasm -g -c *.cubin > /tmp/all_g.sass 2>/dev/null
 python3 - "$K" <<'PY'
 import re, sys
