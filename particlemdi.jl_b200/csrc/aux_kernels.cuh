@@ -173,73 +173,85 @@ extern "C" __global__ void k_broadcast(SweepParams sp) {
 }
 
 // ------------------------------------------------------------------------------------------
-// calc_logmarginal of clusters rebuilt from member lists, one thread per feature, summed over
-// clusters in list order (src/pmdi.jl:358-366); reference formulas gaussian_cluster.jl:68-83,
-// categorical_cluster.jl:53-66, negbinom_cluster.jl:53-60.
-//   out[q] = base[q]*base_sign + sum_c logmarginal_c[q];  flags_out[q] = (1 - 1/exp(out+1)) > u_q
+// calc_logmarginal of clusters rebuilt from member lists (src/pmdi.jl:358-366); reference formulas
+// gaussian_cluster.jl:68-83, categorical_cluster.jl:53-66, negbinom_cluster.jl:53-60.
+// k_logmarginal_part: one thread per (feature, cluster) - the add of a cluster's members is sequential
+// (the reference's operation order), clusters are independent: grid (ceil(D/128), clusters).
+// k_logmarginal: one thread per feature sums the clusters in list order,
+//   out[q] = base[q]*base_scale + sum_c lm[c][q];  flags_out[q] = (1 - 1/exp(out+1)) > u_q
 // ------------------------------------------------------------------------------------------
-extern "C" __global__ void k_logmarginal(DsDev ds, int n_clusters, const int* c_off, const int* members,
-                              const double* gauss_cst /* per cluster */, const double* nlevels,
-                              int use_flags,
+extern "C" __global__ void k_logmarginal_part(DsDev ds, const int* c_off, const int* members,
+                                              const double* gauss_cst /* per cluster */, const double* nlevels,
+                                              int use_flags, double* lm_out /* [clusters][D] */) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+  if (q >= ds.D) return;
+  const bool on = use_flags ? (ds.flag[q] != 0) : true;
+  const int* mem = members + c_off[c];
+  const int cnt = c_off[c + 1] - c_off[c];
+  const double n = (double)cnt;
+  double lm;
+#ifdef PMDI_USER_STRUCT
+  if (ds.type == T_USER) {
+    double st[PmdiUser::WORDS];
+    PmdiUser::init(st);
+    if (on)
+      for (int t = 0; t < cnt; ++t) {
+        const double xv = ds.uW < 0 ? (double)((const int*)ds.x)[(size_t)mem[t] * ds.Dp + q]
+                                    : ((const double*)ds.x)[(size_t)mem[t] * ds.Dp + q];
+        PmdiUser::add(st, t + 1, xv);
+      }
+    lm = PmdiUser::logmarginal(st, cnt);
+  } else
+#endif
+  if (ds.type == T_GAUSSIAN) {
+    double sum = 0.0, beta = 0.5, mu = 0.0;
+    const double* x = (const double*)ds.x;
+    if (on) {
+      // the member's value is fetched two members ahead of the dependent arithmetic
+      double x1 = cnt > 0 ? x[(size_t)mem[0] * ds.Dp + q] : 0.0;
+      double x2 = cnt > 1 ? x[(size_t)mem[1] * ds.Dp + q] : 0.0;
+      for (int t = 0; t < cnt; ++t) {
+        const double nn = (double)(t + 1);
+        const double xv = x1;
+        x1 = x2;
+        if (t + 2 < cnt) x2 = x[(size_t)mem[t + 2] * ds.Dp + q];
+        sum = __dadd_rn(sum, xv);
+        const double dd = __dadd_rn(xv, -mu);
+        beta = __dadd_rn(beta, __ddiv_rn(__dmul_rn(__dadd_rn(__dadd_rn(nn, -1.0), 0.001), __dmul_rn(dd, dd)),
+                                         __dmul_rn(2.0, __dadd_rn(nn, 0.001))));
+        mu = __ddiv_rn(sum, __dadd_rn(nn, 0.001));
+      }
+    }
+    lm = -(n / 2 + 0.5) * log(beta) + gauss_cst[c];
+  } else if (ds.type == T_CATEGORICAL) {
+    const int* x = (const int*)ds.x;
+    const double nl = nlevels[q];  // 0.5 * column maximum (categorical_cluster.jl:10)
+    const int R = (int)(2.0 * nl);
+    lm = lgamma(nl * 2) - lgamma(nl * 2 + n);
+    for (int r = 1; r <= R; ++r) {
+      int cr = 0;
+      if (on)
+        for (int t = 0; t < cnt; ++t) cr += (x[(size_t)mem[t] * ds.Dp + q] == r);
+      lm += lgamma((double)cr + 0.5);
+    }
+  } else {
+    const int* x = (const int*)ds.x;
+    long long S = 0;
+    if (on)
+      for (int t = 0; t < cnt; ++t) S += x[(size_t)mem[t] * ds.Dp + q];
+    lm = lgamma((double)S + 1.0) - lgamma((double)S + (n + 1 + 1)) + lgamma(1.0 + n);
+  }
+  lm_out[(size_t)c * ds.D + q] = lm;
+}
+
+extern "C" __global__ void k_logmarginal(DsDev ds, int n_clusters, const double* lm,
                               const double* base, double base_scale, double out_scale, double* out,
                               uint8_t* flags_out, const double* tape_f, unsigned long long seed,
                               unsigned iter, int k) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= ds.D) return;
   double acc = base ? base[q] * base_scale : 0.0;
-  const bool on = use_flags ? (ds.flag[q] != 0) : true;
-  for (int c = 0; c < n_clusters; ++c) {
-    const int* mem = members + c_off[c];
-    const int cnt = c_off[c + 1] - c_off[c];
-    const double n = (double)cnt;
-    double lm;
-#ifdef PMDI_USER_STRUCT
-    if (ds.type == T_USER) {
-      double st[PmdiUser::WORDS];
-      PmdiUser::init(st);
-      if (on)
-        for (int t = 0; t < cnt; ++t) {
-          const double xv = ds.uW < 0 ? (double)((const int*)ds.x)[(size_t)mem[t] * ds.Dp + q]
-                                      : ((const double*)ds.x)[(size_t)mem[t] * ds.Dp + q];
-          PmdiUser::add(st, t + 1, xv);
-        }
-      lm = PmdiUser::logmarginal(st, cnt);
-    } else
-#endif
-    if (ds.type == T_GAUSSIAN) {
-      double sum = 0.0, beta = 0.5, mu = 0.0;
-      const double* x = (const double*)ds.x;
-      if (on)
-        for (int t = 0; t < cnt; ++t) {
-          const double nn = (double)(t + 1);
-          const double xv = x[(size_t)mem[t] * ds.Dp + q];
-          sum = __dadd_rn(sum, xv);
-          const double dd = __dadd_rn(xv, -mu);
-          beta = __dadd_rn(beta, __ddiv_rn(__dmul_rn(__dadd_rn(__dadd_rn(nn, -1.0), 0.001), __dmul_rn(dd, dd)),
-                                           __dmul_rn(2.0, __dadd_rn(nn, 0.001))));
-          mu = __ddiv_rn(sum, __dadd_rn(nn, 0.001));
-        }
-      lm = -(n / 2 + 0.5) * log(beta) + gauss_cst[c];
-    } else if (ds.type == T_CATEGORICAL) {
-      const int* x = (const int*)ds.x;
-      const double nl = nlevels[q];  // 0.5 * column maximum (categorical_cluster.jl:10)
-      const int R = (int)(2.0 * nl);
-      lm = lgamma(nl * 2) - lgamma(nl * 2 + n);
-      for (int r = 1; r <= R; ++r) {
-        int cr = 0;
-        if (on)
-          for (int t = 0; t < cnt; ++t) cr += (x[(size_t)mem[t] * ds.Dp + q] == r);
-        lm += lgamma((double)cr + 0.5);
-      }
-    } else {
-      const int* x = (const int*)ds.x;
-      long long S = 0;
-      if (on)
-        for (int t = 0; t < cnt; ++t) S += x[(size_t)mem[t] * ds.Dp + q];
-      lm = lgamma((double)S + 1.0) - lgamma((double)S + (n + 1 + 1)) + lgamma(1.0 + n);
-    }
-    acc += lm;
-  }
+  for (int c = 0; c < n_clusters; ++c) acc += lm[(size_t)c * ds.D + q];
   acc *= out_scale;
   out[q] = acc;
   if (flags_out) {
