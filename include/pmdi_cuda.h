@@ -62,8 +62,10 @@ int pmdi_ctx_destroy(pmdi_ctx* ctx);
  *   pmdi_ctx_set_ranks   before the first sweep (after pmdi_ctx_create);
  *   pmdi_ipc_export      after all datasets are bound: the CUDA IPC handle of this rank's arena;
  *   pmdi_ipc_import      all ranks' handles, in rank order (exchange them with any host mechanism).
- * Every rank then calls pmdi_sweep_upload, a host barrier over all ranks, pmdi_sweep_run,
- * pmdi_sweep_download, with identical arguments; every rank returns the same allocations.
+ * Every rank then calls pmdi_sweep (or upload / run / download) with identical arguments, the same number of
+ * times; every rank returns the same allocations.  No host synchronisation between the ranks is needed: the
+ * in-kernel counters and step tags run on from sweep to sweep.  (Only the dense engine, PMDI_ENGINE=dense,
+ * restarts its counters: there a host barrier over all ranks belongs between upload and run.)
  */
 #define PMDI_IPC_HANDLE_BYTES 64
 int pmdi_ctx_set_ranks(pmdi_ctx* ctx, int32_t rank, int32_t n_ranks);
@@ -164,6 +166,10 @@ typedef struct pmdi_sweep_out {
  * pmdi_sweep == pmdi_sweep_upload + pmdi_sweep_run + pmdi_sweep_download.
  */
 int pmdi_sweep(pmdi_ctx* ctx, const pmdi_sweep_args* args, pmdi_sweep_out* out);
+/* upload: validates the arguments, copies them into a pinned block of the context and queues ONE host -> device
+   copy on the context's stream; returns without waiting for the device (the arguments may be reused at once;
+   a second upload waits until the first one's copy has left the pinned block).  download: queues ONE
+   device -> host copy of the result block, synchronises the stream, hands the results out. */
 int pmdi_sweep_upload(pmdi_ctx* ctx, const pmdi_sweep_args* args);   /* host -> device inputs   */
 int pmdi_sweep_run(pmdi_ctx* ctx);                                   /* asynchronous, on stream */
 int pmdi_sweep_download(pmdi_ctx* ctx, pmdi_sweep_out* out);         /* sync + device -> host   */
