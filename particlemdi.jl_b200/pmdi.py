@@ -88,6 +88,9 @@ class HyperTables:
         self.phi_index = (np.stack([self.combn[:, a] == self.combn[:, b] for a, b in pairs], axis=1)
                           if K > 1 else np.ones((rows, 1), dtype=bool))
         self.log_gamma_sum = None
+        # rows of every (dataset, label), ascending: what `col == n` selects (update_hypers.jl:75-78)
+        self.rows_of = [[np.flatnonzero(self.combn[:, k] == n) for n in range(N)] for k in range(K)]
+        self.rows_pair = [np.flatnonzero(self.phi_index[:, i]) for i in range(self.phi_index.shape[1])]
 
     def refresh(self, gamma):
         """sum(Gamma_c, dims=2): sum_k log gamma[c_k, k] per combination."""
@@ -214,18 +217,30 @@ def update_v(n_obs, Z, rng):
     return float(rng.gamma(n_obs, 1.0 / Z))
 
 
+def _gamma_logpdf(x, a, scale):
+    """scipy.stats.gamma.logpdf(x, a=a, scale=scale) for x > 0, spelled out (same operations in the same order,
+    same bits; the generic rv_continuous wrapper costs ~100 us a call)."""
+    y = x / scale
+    return (special.xlogy(a - 1.0, y) - y - special.gammaln(a)) - math.log(scale)
+
+
+def _binom_logpmf(j, n, p):
+    """scipy.stats.binom.logpmf(j, n, p) for integer 0 <= j <= n, spelled out (same operations, same bits)."""
+    combiln = special.gammaln(n + 1) - (special.gammaln(j + 1) + special.gammaln(n - j + 1))
+    return combiln + special.xlogy(j, p) + special.xlog1py(n - j, -p)
+
+
 def update_M(M, gamma, K, N, rng):
     """update_M! (src/update_hypers.jl:5-26): random-walk Metropolis on each mass parameter,
     prior Gamma(2, 0.25)."""
     for k in range(K):
         g, cur = gamma[:, k], M[k]
-        ll = stats.gamma.logpdf(g, a=cur / N, scale=1.0).sum() + stats.gamma.logpdf(cur, a=2.0, scale=0.25)
+        ll = _gamma_logpdf(g, cur / N, 1.0).sum() + _gamma_logpdf(cur, 2.0, 0.25)
         prop = cur + rng.normal() / 10.0
         if prop <= 0.0:
             alpha = 0.0
         else:
-            ll_new = (stats.gamma.logpdf(g, a=prop / N, scale=1.0).sum()
-                      + stats.gamma.logpdf(prop, a=2.0, scale=0.25))
+            ll_new = _gamma_logpdf(g, prop / N, 1.0).sum() + _gamma_logpdf(prop, 2.0, 0.25)
             alpha = math.exp(min(ll_new - ll, 50.0))
         if rng.random() < alpha:
             M[k] = prop
@@ -247,9 +262,8 @@ def update_gamma(gamma, phi, v, M, s, tables, rng, counts_all=None):
     norm = tables.norm_terms(phi)
     for k in range(K):
         counts = counts_all[:, k] if counts_all is not None else np.bincount(s[:, k] - 1, minlength=N)  # countn(s[:, k], n), :72
-        col = tables.combn[:, k]
         for n in range(N):
-            rows = col == n
+            rows = tables.rows_of[k][n]  # ascending indices: the same elements in the same order as the mask `col == n`
             old = gamma[n, k]
             beta_star = 1.0 + v * norm[rows].sum() / old
             gamma[n, k] = rng.gamma(M[k] / N + counts[n], 1.0 / beta_star) + EPS
@@ -270,10 +284,10 @@ def update_phi(phi, v, s, tables, rng, agree_all=None, gamma=None):
         if fact:
             beta_star = 5.0 + v * tables.Q(gamma, phi, i)
         else:
-            rows = tables.phi_index[:, i]
+            rows = tables.rows_pair[i]
             beta_star = 5.0 + v * norm[rows].sum() / (1.0 + cur)
         j = np.arange(n_agree + 1)
-        w = special.gammaln(j + 1.0) + stats.binom.logpmf(j, n_agree, 0.5) - j * math.log(1.0 / beta_star)
+        w = special.gammaln(j + 1.0) + _binom_logpmf(j, n_agree, 0.5) - j * math.log(1.0 / beta_star)
         w = np.exp(w - w.max())
         alpha_star = 1.0 + rng.choice(n_agree + 1, p=w / w.sum())
         phi[i] = rng.gamma(alpha_star, 1.0 / beta_star)
@@ -342,12 +356,20 @@ def align_labels_tables(s, cont, phi, gamma, N, K, rng):
             label = lab0 - 1
             if size[label] == 0:
                 continue
+            # one uniform per proposal, drawn as the reference does (N - 1 or N proposals per processed label; a block
+            # draw is the same stream as scalar draws); the log-ratios of all proposals of the current
+            # label come from W in one expression and are recomputed after an accepted swap
+            u = rng.random(N - 1).tolist()
+            ui = 0
+            delta = ((W[label, :] + W[:, label]) - (W[label, label] + np.diagonal(W))).tolist()
             for new_label in range(N):
                 if new_label == label:
                     continue
-                keep = W[label, label] + W[new_label, new_label]
-                swap = W[label, new_label] + W[new_label, label]
-                if rng.random() < math.exp(min(swap - keep, 50.0)):
+                if ui == len(u):  # a swap before the label's own index was reached: that index is proposed too
+                    u.append(rng.random())
+                accept = u[ui] < math.exp(min(delta[new_label], 50.0))
+                ui += 1
+                if accept:
                     W[[label, new_label]] = W[[new_label, label]]
                     T[:, [label, new_label]] = T[:, [new_label, label]]
                     size[[label, new_label]] = size[[new_label, label]]
@@ -356,6 +378,7 @@ def align_labels_tables(s, cont, phi, gamma, N, K, rng):
                     a_, b_ = perm == label, perm == new_label
                     perm[a_], perm[b_] = new_label, label
                     label = new_label
+                    delta = ((W[label, :] + W[:, label]) - (W[label, label] + np.diagonal(W))).tolist()
         s[:, k] = perm[s[:, k] - 1] + 1
         for ji, j in enumerate(others):  # the other datasets see dataset k's new labels
             if k < j:
@@ -394,7 +417,7 @@ def csv_header(K, n_obs, dataNames):
 def csv_row(M, phi, ll, s):
     """[M; Phi; ll; vec(s)] promoted to Float64 (labels print as ``3.0``), dataset-major."""
     vals = [_jl(v) for v in M] + [_jl(v) for v in phi] + [_jl(ll)]
-    vals += [f"{int(v)}.0" for v in np.asarray(s).reshape(-1, order="F")]
+    vals += [f"{v}.0" for v in np.asarray(s).reshape(-1, order="F").tolist()]
     return ",".join(vals)
 
 
