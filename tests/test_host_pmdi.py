@@ -217,3 +217,31 @@ def test_align_labels_from_tables_equals_align_labels(K):
         np.testing.assert_array_equal(counts[:, k], np.bincount(s2[:, k] - 1, minlength=N))
     for i, (a, b) in enumerate(pairs):
         assert agree[i] == (s2[:, a] == s2[:, b]).sum()
+
+
+def test_spelled_out_log_densities_are_scipy_bit_for_bit():
+    """update_M! / update_Phi! (src/update_hypers.jl:5-26, 95-128) use the gamma and binomial log-densities; the
+    host loop spells scipy's formulas out (the generic wrappers cost ~100 us a call).  Same bits required: the
+    values decide Metropolis tests and mixture draws."""
+    from scipy import stats
+    rng = np.random.default_rng(11)
+    for _ in range(300):
+        x = rng.gamma(0.05, 1.0, 20) + host.EPS
+        a = rng.uniform(0.01, 5.0)
+        np.testing.assert_array_equal(stats.gamma.logpdf(x, a=a, scale=1.0), host._gamma_logpdf(x, a, 1.0))
+        c = rng.uniform(0.01, 30.0)
+        assert stats.gamma.logpdf(c, a=2.0, scale=0.25) == host._gamma_logpdf(c, 2.0, 0.25)
+        n = int(rng.integers(0, 2500))
+        j = np.arange(n + 1)
+        np.testing.assert_array_equal(stats.binom.logpmf(j, n, 0.5), host._binom_logpmf(j, n, 0.5))
+
+
+def test_row_lists_of_the_tables_are_the_masks():
+    """update_gamma! / update_Phi! sum the normalising terms over the rows with c_k = n / c_a = c_b
+    (src/update_hypers.jl:75-78, 101-104): the precomputed row lists select what the masks select, in order."""
+    t = host.HyperTables(5, 3)
+    for k in range(3):
+        for n in range(5):
+            np.testing.assert_array_equal(t.rows_of[k][n], np.flatnonzero(t.combn[:, k] == n))
+    for i in range(3):
+        np.testing.assert_array_equal(t.rows_pair[i], np.flatnonzero(t.phi_index[:, i]))
