@@ -542,7 +542,7 @@ def pmdi(dataFiles, dataTypes, N, particles, rho, iter, outputFile, *, thin=1, f
                 do_sweep = ctx.sweep_sharded if world > 1 else ctx.sweep
                 r = do_sweep(s, order_obs, n1, Pi, phi if K > 1 else None,
                              logweight_init=0.0 if it == 1 else 1.0,   # :99, :372
-                             seed=seed, it=it, sstar_compat=sstar_compat)  # :188-350, :373
+                             seed=seed, it=it, sstar_compat=sstar_compat, cluster_sizes=False)  # :188-350, :373
                 s = np.array(r["s"], dtype=np.int64, order="C")
                 stats_out["sweep_device_ms"] += r["device_ms"]
                 stats_out["n_resamples"] += r["n_resamples"]
