@@ -65,3 +65,22 @@ def test_uniform_is_the_oracles_philox():
     from oracle import oracle as orc
     for args in [(1, 0, 0, 0, 0, 1), (2 ** 40 + 5, 7, 2, 300, 0, 99), (42, 3, 4, 0, 2, 1999)]:
         assert capi.uniform(*args) == orc.uniform(*args)
+
+
+def test_sweep_kernel_resources_stay_within_the_measured_build():
+    """The persistent sweep kernel is bound by per-step latency; a change in code it never executes moved every step
+    by 13 % once, through the whole-kernel register allocation (stack frame 352 -> 848 bytes,
+    profiles/r02_spec_kernel.md).  Guard: the production instantiation keeps 128 registers (one 512-thread CTA per SM)
+    and a stack frame no larger than the measured build's."""
+    import re
+    import shutil
+    import subprocess
+    tool = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(tool):
+        pytest.skip("cuobjdump not available")
+    out = subprocess.run([tool, "--dump-resource-usage", capi.LIB_PATH], capture_output=True, text=True).stdout
+    m = re.search(r"Function k_sweep_spec:\s*\n\s*REG:(\d+) STACK:(\d+)", out)
+    assert m, "k_sweep_spec not found in the library"
+    regs, stack = int(m.group(1)), int(m.group(2))
+    assert regs <= 128
+    assert stack <= 384, f"k_sweep_spec stack frame {stack} B (measured build: 352 B): time it A/B before shipping (scripts/gpu_ab.sh)"
